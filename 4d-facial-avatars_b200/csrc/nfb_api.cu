@@ -1,0 +1,280 @@
+// nfb_api.cu — the C ABI declared in include/nfb.h: handle management, argument validation, and
+// translation of the public structs into kernel launches.  No torch, no exceptions across the boundary.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/nfb.h"
+#include "nfb_internal.h"
+#include "nfb_layout.h"
+
+namespace {
+thread_local std::string g_last_cuda_error;
+
+int cuda_fail(cudaError_t e, const char* where) {
+  g_last_cuda_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return NFB_ERR_CUDA;
+}
+#define NFB_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+template <class T>
+cudaError_t dev_alloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+}  // namespace
+
+struct NfbHandle {
+  int device = 0;
+  int num_sms = 0;
+  nfb::NetBuffers net[2];
+  bool frame_set = false;
+  long long launches = 0;
+  // cached torch.linspace(0,1,n) tables on the device
+  float* lin_c = nullptr; int lin_c_n = 0;
+  float* lin_f = nullptr; int lin_f_n = 0;
+  // staging for nfb_render_frame_host
+  float *d_expr = nullptr, *d_latent = nullptr, *d_bg = nullptr, *d_out = nullptr;
+  size_t bg_cap = 0, out_cap = 0;
+};
+
+extern "C" {
+
+int nfb_version(void) { return NFB_VERSION; }
+
+const char* nfb_strerror(int status) {
+  switch (status) {
+    case NFB_OK: return "ok";
+    case NFB_ERR_INVALID: return "invalid argument";
+    case NFB_ERR_UNSUPPORTED: return "configuration not supported by the sm_100a render kernel";
+    case NFB_ERR_CUDA: return "CUDA runtime error (see nfb_last_cuda_error)";
+    case NFB_ERR_STATE: return "weights or per-frame conditioning not set";
+    case NFB_ERR_ARCH: return "device is not compute capability 10.x (sm_100a code only)";
+    default: return "unknown status";
+  }
+}
+
+const char* nfb_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+int nfb_host_linspace(float* out, int n) {
+  if (!out || n < 1) return NFB_ERR_INVALID;
+  if (n == 1) { out[0] = 0.f; return NFB_OK; }
+  // ATen's CPU linspace: symmetric evaluation about the midpoint, all in FP32.
+  const float start = 0.f, end = 1.f;
+  const float step = (end - start) / static_cast<float>(n - 1);
+  const int halfway = n / 2;
+  for (int i = 0; i < n; ++i) out[i] = (i < halfway) ? start + step * static_cast<float>(i) : end - step * static_cast<float>(n - i - 1);
+  return NFB_OK;
+}
+
+int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
+  if (!dims || !out) return NFB_ERR_INVALID;
+  if (dims->num_encoding_fn_xyz != 10 || dims->num_encoding_fn_dir != 4 || dims->include_input_xyz != 1 ||
+      dims->include_input_dir != 0 || dims->dim_expression != nfb::kDimExpr || dims->dim_latent != nfb::kDimLatent)
+    return NFB_ERR_UNSUPPORTED;
+  NFB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  NFB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return NFB_ERR_ARCH;
+  NfbHandle* h = new (std::nothrow) NfbHandle();
+  if (!h) return NFB_ERR_INVALID;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  for (int n = 0; n < 2; ++n) {
+    nfb::NetBuffers& nb = h->net[n];
+    NFB_CUDA(dev_alloc(&nb.stream_x1, nfb::kStreamBytesX1));
+    NFB_CUDA(dev_alloc(&nb.stream_x3, nfb::kStreamBytesX3));
+    NFB_CUDA(dev_alloc(&nb.w6, 144 * 256));
+    NFB_CUDA(dev_alloc(&nb.b6, 144));
+    NFB_CUDA(dev_alloc(&nb.bias_static, nfb::kBiasFloats));
+    NFB_CUDA(dev_alloc(&nb.bias_frame, nfb::kBiasFloats));
+    NFB_CUDA(dev_alloc(&nb.w0c, 256 * nfb::kDimCond));
+    NFB_CUDA(dev_alloc(&nb.w3c, 256 * nfb::kDimCond));
+    NFB_CUDA(dev_alloc(&nb.wd0b_t, nfb::kDimDir * 128));
+  }
+  NFB_CUDA(dev_alloc(&h->d_expr, nfb::kDimExpr));
+  NFB_CUDA(dev_alloc(&h->d_latent, nfb::kDimLatent));
+  NFB_CUDA(nfb::render_kernel_setup());
+  *out = h;
+  return NFB_OK;
+}
+
+int nfb_destroy(NfbHandle* h) {
+  if (!h) return NFB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  for (int n = 0; n < 2; ++n) {
+    nfb::NetBuffers& nb = h->net[n];
+    cudaFree(nb.stream_x1); cudaFree(nb.stream_x3); cudaFree(nb.w6); cudaFree(nb.b6); cudaFree(nb.bias_static);
+    cudaFree(nb.bias_frame); cudaFree(nb.w0c); cudaFree(nb.w3c); cudaFree(nb.wd0b_t);
+  }
+  cudaFree(h->lin_c); cudaFree(h->lin_f); cudaFree(h->d_expr); cudaFree(h->d_latent); cudaFree(h->d_bg); cudaFree(h->d_out);
+  delete h;
+  return NFB_OK;
+}
+
+int nfb_load_weights(NfbHandle* h, int which, const float* const params[26], void* stream) {
+  if (!h || !params || (which != NFB_NET_COARSE && which != NFB_NET_FINE)) return NFB_ERR_INVALID;
+  for (int i = 0; i < 26; ++i)
+    if (!params[i]) return NFB_ERR_INVALID;
+  NFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  nfb::NetBuffers& nb = h->net[which];
+  NFB_CUDA(nfb::launch_load_weights(nb, params, st, &h->launches));
+  nb.loaded = true;
+  h->frame_set = false;  // folded biases are stale
+  return NFB_OK;
+}
+
+int nfb_set_frame(NfbHandle* h, const float* expression, const float* latent, void* stream) {
+  if (!h || !expression || !latent) return NFB_ERR_INVALID;
+  if (!h->net[0].loaded) return NFB_ERR_STATE;
+  NFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int n = 0; n < 2; ++n)
+    if (h->net[n].loaded) NFB_CUDA(nfb::launch_frame_fold(h->net[n], expression, latent, st, &h->launches));
+  h->frame_set = true;
+  return NFB_OK;
+}
+
+static int ensure_linspace(float** buf, int* cached_n, int n, cudaStream_t st) {
+  if (*cached_n == n && *buf) return NFB_OK;
+  std::vector<float> host(n);
+  nfb_host_linspace(host.data(), n);
+  if (*buf) NFB_CUDA(cudaFree(*buf));
+  *buf = nullptr;
+  *cached_n = 0;
+  NFB_CUDA(dev_alloc(buf, (size_t)n));
+  // pageable source: the runtime stages it before returning, so `host` may die afterwards
+  NFB_CUDA(cudaMemcpyAsync(*buf, host.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+  *cached_n = n;
+  return NFB_OK;
+}
+
+int nfb_render_forward(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm, const NfbNoise* noise, const NfbOutputs* out,
+                       const NfbDebug* dbg, void* stream) {
+  if (!h || !rays || !sm || !out) return NFB_ERR_INVALID;
+  if (rays->n_rays < 0) return NFB_ERR_INVALID;
+  if ((rays->o == nullptr) != (rays->d == nullptr)) return NFB_ERR_INVALID;
+  if (!rays->o && (rays->width <= 0 || rays->height <= 0)) return NFB_ERR_INVALID;
+  const int nc = sm->num_coarse, nf = sm->num_fine;
+  if (nc < 3 || nf < 0 || nc + nf > 1024) return NFB_ERR_UNSUPPORTED;
+  if (sm->lindisp) return NFB_ERR_UNSUPPORTED;
+  if (sm->precision != NFB_PREC_FAST && sm->precision != NFB_PREC_EXACT) return NFB_ERR_INVALID;
+  if (!h->net[0].loaded || (nf > 0 && !h->net[1].loaded) || !h->frame_set) return NFB_ERR_STATE;
+  if (!out->rgb_coarse || !out->disp_coarse || !out->acc_coarse) return NFB_ERR_INVALID;
+  if (nf > 0 && (!out->rgb_fine || !out->disp_fine || !out->acc_fine)) return NFB_ERR_INVALID;
+  if (sm->perturb && (!noise || !noise->t_rand || (nf > 0 && !noise->u))) return NFB_ERR_INVALID;
+  if (sm->noise_std > 0.f && (!noise || !noise->sigma_noise_c || (nf > 0 && !noise->sigma_noise_f))) return NFB_ERR_INVALID;
+  if (rays->n_rays == 0) return NFB_OK;
+  NFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  nfb::RenderParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.o = rays->o; p.d = rays->d; p.n_rays = rays->n_rays;
+  for (int i = 0; i < 12; ++i) p.pose[i] = rays->pose[i];
+  p.fx = static_cast<float>(rays->intrinsics[0]);
+  p.fy = static_cast<float>(rays->intrinsics[1]);
+  p.wcx = static_cast<float>(static_cast<double>(rays->width) * rays->intrinsics[2]);
+  p.hcy = static_cast<float>(static_cast<double>(rays->height) * rays->intrinsics[3]);
+  p.width = rays->width > 0 ? rays->width : 1;
+  p.row_begin = rays->row_begin;
+  p.near_ = rays->near_; p.far_ = rays->far_;
+  p.dir_z = rays->dir_z; p.bg = rays->background;
+  p.nc = nc; p.nf = nf; p.s_fine = nc + nf;
+  p.rays_per_unit = (2 * (nc + nf) <= 1024) ? 2 : 1;
+  p.tiles_c = (p.rays_per_unit * nc + 127) / 128;
+  p.tiles_f = nf > 0 ? (p.rays_per_unit * (nc + nf) + 127) / 128 : 0;
+  p.n_units = (rays->n_rays + p.rays_per_unit - 1) / p.rays_per_unit;
+  p.perturb = sm->perturb ? 1 : 0;
+  p.noise_std = sm->noise_std;
+  p.white_bkgd = sm->white_background ? 1 : 0;
+  if (sm->t_coarse) p.t_coarse = sm->t_coarse;
+  else {
+    int rc = ensure_linspace(&h->lin_c, &h->lin_c_n, nc, st);
+    if (rc) return rc;
+    p.t_coarse = h->lin_c;
+  }
+  if (nf > 0) {
+    if (sm->u_fine) p.u_fine = sm->u_fine;
+    else {
+      int rc = ensure_linspace(&h->lin_f, &h->lin_f_n, nf, st);
+      if (rc) return rc;
+      p.u_fine = h->lin_f;
+    }
+  }
+  if (noise) { p.t_rand = noise->t_rand; p.noise_c = noise->sigma_noise_c; p.u_rand = noise->u; p.noise_f = noise->sigma_noise_f; }
+  const bool exact = sm->precision == NFB_PREC_EXACT;
+  for (int n = 0; n < 2; ++n) {
+    p.wstream[n] = exact ? h->net[n].stream_x3 : h->net[n].stream_x1;
+    p.bias[n] = h->net[n].bias_frame;
+    p.wd0b_t[n] = h->net[n].wd0b_t;
+  }
+  if (nf == 0) { p.wstream[1] = p.wstream[0]; p.bias[1] = p.bias[0]; p.wd0b_t[1] = p.wd0b_t[0]; }
+  p.rgb_c = out->rgb_coarse; p.disp_c = out->disp_coarse; p.acc_c = out->acc_coarse;
+  p.rgb_f = out->rgb_fine; p.disp_f = out->disp_fine; p.acc_f = out->acc_fine; p.w_last = out->w_last;
+  if (dbg) {
+    p.dbg_z_c = dbg->z_coarse; p.dbg_raw_c = dbg->raw_coarse; p.dbg_z_f = dbg->z_fine; p.dbg_raw_f = dbg->raw_fine;
+    p.dbg_act = dbg->act_dump; p.dbg_act_step = dbg->act_step;
+  }
+  NFB_CUDA(nfb::launch_render(p, exact ? 1 : 0, h->num_sms, st, &h->launches));
+  return NFB_OK;
+}
+
+int nfb_render_frame_host(NfbHandle* h, const float pose[12], const double intrinsics[4], int height, int width, int row_begin,
+                          int rows, float near_, float far_, const float* expression_host, const float* latent_host,
+                          const float* background_host, const NfbSampling* sm, float* out_host, void* stream) {
+  if (!h || !pose || !intrinsics || !expression_host || !latent_host || !sm || !out_host) return NFB_ERR_INVALID;
+  if (height <= 0 || width <= 0 || rows <= 0 || row_begin < 0 || row_begin + rows > height) return NFB_ERR_INVALID;
+  if (sm->perturb || sm->noise_std > 0.f) return NFB_ERR_UNSUPPORTED;  // host path is the deterministic renderer
+  NFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)rows * width;
+  if (h->out_cap < 11 * n) {
+    if (h->d_out) NFB_CUDA(cudaFree(h->d_out));
+    h->d_out = nullptr; h->out_cap = 0;
+    NFB_CUDA(dev_alloc(&h->d_out, 11 * n));
+    h->out_cap = 11 * n;
+  }
+  if (background_host && h->bg_cap < 3 * n) {
+    if (h->d_bg) NFB_CUDA(cudaFree(h->d_bg));
+    h->d_bg = nullptr; h->bg_cap = 0;
+    NFB_CUDA(dev_alloc(&h->d_bg, 3 * n));
+    h->bg_cap = 3 * n;
+  }
+  NFB_CUDA(cudaMemcpyAsync(h->d_expr, expression_host, nfb::kDimExpr * sizeof(float), cudaMemcpyHostToDevice, st));
+  NFB_CUDA(cudaMemcpyAsync(h->d_latent, latent_host, nfb::kDimLatent * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (background_host) NFB_CUDA(cudaMemcpyAsync(h->d_bg, background_host, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = nfb_set_frame(h, h->d_expr, h->d_latent, stream);
+  if (rc) return rc;
+  NfbRays r;
+  std::memset(&r, 0, sizeof(r));
+  r.n_rays = (int)n;
+  for (int i = 0; i < 12; ++i) r.pose[i] = pose[i];
+  for (int i = 0; i < 4; ++i) r.intrinsics[i] = intrinsics[i];
+  r.height = height; r.width = width; r.row_begin = row_begin;
+  r.near_ = near_; r.far_ = far_;
+  r.background = background_host ? h->d_bg : nullptr;
+  NfbOutputs o;
+  float* b = h->d_out;
+  o.rgb_coarse = b; o.disp_coarse = b + 3 * n; o.acc_coarse = b + 4 * n;
+  o.rgb_fine = b + 5 * n; o.disp_fine = b + 8 * n; o.acc_fine = b + 9 * n; o.w_last = b + 10 * n;
+  rc = nfb_render_forward(h, &r, sm, nullptr, &o, nullptr, stream);
+  if (rc) return rc;
+  NFB_CUDA(cudaMemcpyAsync(out_host, h->d_out, 11 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  NFB_CUDA(cudaStreamSynchronize(st));
+  return NFB_OK;
+}
+
+int nfb_launch_count(NfbHandle* h, long long* out) {
+  if (!h || !out) return NFB_ERR_INVALID;
+  *out = h->launches;
+  return NFB_OK;
+}
+
+}  // extern "C"

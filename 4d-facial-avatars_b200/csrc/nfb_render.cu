@@ -1,0 +1,677 @@
+// nfb_render.cu — the per-ray hot path as ONE persistent sm_100a kernel.
+//
+// Reference path replaced (nerface_code/nerf-pytorch/nerf/):
+//   train_utils.py:36-162  predict_and_render_radiance   (sampling, coarse->fine control flow)
+//   train_utils.py:9-33    run_network                    (encode + MLP over all samples)
+//   nerf_helpers.py:195-239 positional_encoding, :344-387 sample_pdf_2, :44-65 cumprod_exclusive,
+//   nerf_helpers.py:68-123 get_ray_bundle (optional in-kernel ray generation)
+//   volume_rendering_utils.py:7-75 volume_render_radiance_field
+//   models.py:236-261      ConditionalBlendshapePaperNeRFModel.forward
+//
+// Work decomposition.  A "unit" is R (1 or 2) rays.  One CTA per SM loops over units; per unit it runs
+// the coarse pass (R*Nc sample rows) and the fine pass (R*(Nc+Nf) rows) as 128-row tensor-core tiles.
+// Per tile the MLP is 10 GEMM steps (nfb_layout.h): accumulators live in TMEM, hidden activations are
+// written back to TMEM as FP16 (tcgen05.st) and consumed as the A operand of the next step straight
+// from TMEM, weights stream L2 -> shared memory through the bulk-copy (TMA) engine into an 8-slot ring
+// of pre-swizzled 16 KB units.
+//
+// Warp roles (192 threads): warp 0 lane 0 = weight producer, warp 1 lane 0 = tcgen05.mma issuer (warp 1
+// also owns the TMEM allocation), warps 2..5 = "row" warps: thread <-> TMEM lane <-> sample row.  They
+// do sampling, positional encoding, per-step epilogues (bias, ReLU, FP16 split), compositing,
+// inverse-CDF resampling and the per-ray sort.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "nfb_internal.h"
+#include "nfb_layout.h"
+#include "nfb_ptx.cuh"
+
+namespace nfb {
+
+constexpr int kNumSlots = 8;
+constexpr int kRowsMax = 1024;  // sample rows of one pass of one unit
+constexpr int kThreads = 192;
+constexpr int kRowThreads = 128;
+constexpr uint32_t kRowBarrier = 1;  // named barrier id of the four row warps
+
+// TMEM column map (512 columns x 128 lanes x 32 bit)
+constexpr uint32_t kColAcc = 0;    // FP32 accumulators: half 0 at +0, half 1 at +128
+constexpr uint32_t kColAhi = 256;  // FP16 activations (hi part), 2 K-elements per column, 128 columns
+constexpr uint32_t kColAlo = 384;  // FP16 activations (lo part), exact mode only
+
+// shared memory map (bytes from the 1024-aligned base)
+constexpr int kOffRing = 0;
+constexpr int kOffPeHi = kOffRing + kNumSlots * kMaxUnitBytes;
+constexpr int kOffPeLo = kOffPeHi + kTileM * 128;
+constexpr int kOffBias = kOffPeLo + kTileM * 128;
+constexpr int kOffRaw = kOffBias + 2 * kBiasFloats * 4;
+constexpr int kOffZ = kOffRaw + kRowsMax * 16;
+constexpr int kOffW = kOffZ + kRowsMax * 4;
+constexpr int kOffCdf = kOffW + kRowsMax * 4;
+constexpr int kOffBins = kOffCdf + kRowsMax * 4;
+constexpr int kOffSort = kOffBins + kRowsMax * 4;
+constexpr int kOffDirBias = kOffSort + kRowsMax * 4;
+constexpr int kRayFloats = 40;  // o[3] d[3] dnorm valid bg[3] pad PEd[24] ... (see RayP)
+constexpr int kOffRay = kOffDirBias + 2 * 128 * 4;
+constexpr int kOffBars = kOffRay + 2 * kRayFloats * 4;
+constexpr int kNumBars = 2 * kNumSlots + 2;
+constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;  // + slack for the 1024-byte alignment
+static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0, "alignment");
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+
+struct RayP {  // per-ray constants in shared memory (kRayFloats floats)
+  float o[3], d[3];
+  float dnorm;
+  int valid;
+  float bg[3];
+  int gidx;
+  float ped[24];
+  float pad[4];
+};
+static_assert(sizeof(RayP) == kRayFloats * 4, "RayP size");
+
+__device__ const int kStepOff[kNumSteps] = {step_offset_x1(0), step_offset_x1(1), step_offset_x1(2), step_offset_x1(3),
+                                            step_offset_x1(4), step_offset_x1(5), step_offset_x1(6), step_offset_x1(7),
+                                            step_offset_x1(8), step_offset_x1(9)};
+
+// ------------------------------------------------------------------------------------------------
+// sin/cos of y for the positional encoding.  The reference evaluates torch.sin(x * 2^k) in FP32
+// (nerf_helpers.py:231-233); x * 2^k is exact, so both variants see the same argument.
+//   exact: libdevice sinf/cosf (<= 2 ulp).
+//   fast : two-constant Cody-Waite reduction to [-pi, pi] + MUFU.SIN/COS (abs err ~5e-7), well below the
+//          FP16 rounding (2.4e-4) the value then receives.
+template <bool EXACT>
+__device__ __forceinline__ void pe_sincos(float y, float& s, float& c) {
+  if constexpr (EXACT) {
+    sincosf(y, &s, &c);
+  } else {
+    const float n = rintf(y * 0.15915494309189535f);
+    float r = fmaf(-n, 6.2831854820251465f, y);
+    r = fmaf(-n, -1.7484555e-7f, r);
+    s = __sinf(r);
+    c = __cosf(r);
+  }
+}
+
+// Write one row of the 64-lane positional encoding into the swizzled PE buffer(s).
+template <bool EXACT>
+__device__ __forceinline__ void store_pe_row(uint8_t* pe_hi, uint8_t* pe_lo, int row, const float (&f)[64]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = f[q * 8 + 2 * e], b = f[q * 8 + 2 * e + 1];
+      hi[e] = pack_f16x2(a, b);
+      if constexpr (EXACT) {
+        const float2 hf = unpack_f16x2(hi[e]);
+        lo[e] = pack_f16x2(a - hf.x, b - hf.y);
+      }
+    }
+    const int off = row * 128 + ((q ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(pe_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if constexpr (EXACT) *reinterpret_cast<uint4*>(pe_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one 32-column accumulator chunk: v = relu(acc + bias (+ extra)); FP16 (hi[,lo]) -> TMEM A.
+template <bool EXACT>
+__device__ __forceinline__ void epi_chunk(uint32_t t_acc, uint32_t t_ahi, uint32_t t_alo, const float* __restrict__ bias,
+                                          const float* __restrict__ extra, float* __restrict__ dump) {
+  uint32_t v[32];
+  tmem_ld32(t_acc, v);
+  tmem_wait_ld();
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + j);
+    float x0 = __uint_as_float(v[j]) + b.x, x1 = __uint_as_float(v[j + 1]) + b.y;
+    float x2 = __uint_as_float(v[j + 2]) + b.z, x3 = __uint_as_float(v[j + 3]) + b.w;
+    if (extra) {
+      const float4 e = *reinterpret_cast<const float4*>(extra + j);
+      x0 += e.x; x1 += e.y; x2 += e.z; x3 += e.w;
+    }
+    x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+    if (dump) { dump[j] = x0; dump[j + 1] = x1; dump[j + 2] = x2; dump[j + 3] = x3; }
+    hi[j / 2] = pack_f16x2(x0, x1);
+    hi[j / 2 + 1] = pack_f16x2(x2, x3);
+    if constexpr (EXACT) {
+      const float2 h0 = unpack_f16x2(hi[j / 2]), h1 = unpack_f16x2(hi[j / 2 + 1]);
+      lo[j / 2] = pack_f16x2(x0 - h0.x, x1 - h0.y);
+      lo[j / 2 + 1] = pack_f16x2(x2 - h1.x, x3 - h1.y);
+    }
+  }
+  tmem_st16(t_ahi, hi);
+  if constexpr (EXACT) tmem_st16(t_alo, lo);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compositing of one ray by one warp (volume_rendering_utils.py:7-75).  Samples are lane-blocked.
+// raw/z/wbuf index the pass-local row of the ray's first sample.  Returns w of the last sample in
+// every lane.  Writes rgb[3], disp, acc through the given pointers from lane 0 (if non-null).
+__device__ __forceinline__ float composite_ray(const float4* __restrict__ raw, const float* __restrict__ z, float* __restrict__ wbuf,
+                                               int S, const RayP& rp, bool has_bg, float noise_std, const float* __restrict__ noise,
+                                               bool white_bkgd, float* out_rgb, float* out_disp, float* out_acc, int lane) {
+  const int per = (S + 31) >> 5;
+  const int i0 = lane * per;
+  // pass 1: alpha per sample (kept in wbuf), product of (1 - alpha + 1e-10) over this lane's block
+  float prod = 1.f;
+  for (int j = 0; j < per; ++j) {
+    const int i = i0 + j;
+    if (i < S) {
+      const float zi = z[i];
+      float delta = (i < S - 1) ? __fsub_rn(z[i + 1], zi) : 1e10f;
+      delta = __fmul_rn(delta, rp.dnorm);
+      float sig = raw[i].w;
+      if (noise_std > 0.f) sig = __fadd_rn(sig, __fmul_rn(noise[i], noise_std));
+      sig = fmaxf(sig, 0.f);
+      if (i == S - 1) sig = __fadd_rn(sig, 1e-6f);
+      const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(sig, delta)));
+      wbuf[i] = alpha;
+      prod *= __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+    }
+  }
+  // exclusive multiplicative scan over lanes
+  float incl = prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= t;
+  }
+  float T = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) T = 1.f;
+  // pass 2: weights and weighted sums
+  float r = 0.f, g = 0.f, b = 0.f, depth = 0.f, acc = 0.f, wl = 0.f;
+  for (int j = 0; j < per; ++j) {
+    const int i = i0 + j;
+    if (i < S) {
+      const float alpha = wbuf[i];
+      const float w = __fmul_rn(alpha, T);
+      T *= __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+      wbuf[i] = w;
+      float cr, cg, cb;
+      if (has_bg && i == S - 1) {
+        cr = rp.bg[0]; cg = rp.bg[1]; cb = rp.bg[2];  // background colour is NOT squashed (:29-33)
+      } else {
+        const float4 q = raw[i];
+        cr = 1.f / (1.f + expf(-q.x));
+        cg = 1.f / (1.f + expf(-q.y));
+        cb = 1.f / (1.f + expf(-q.z));
+      }
+      r = fmaf(w, cr, r); g = fmaf(w, cg, g); b = fmaf(w, cb, b);
+      depth = fmaf(w, z[i], depth);
+      acc += w;
+      if (i == S - 1) wl = w;
+    }
+  }
+  r = warp_sum(r); g = warp_sum(g); b = warp_sum(b);
+  depth = warp_sum(depth); acc = warp_sum(acc); wl = warp_sum(wl);
+  if (lane == 0 && out_rgb) {
+    if (white_bkgd) { r += 1.f - acc; g += 1.f - acc; b += 1.f - acc; }
+    out_rgb[0] = r; out_rgb[1] = g; out_rgb[2] = b;
+    *out_disp = 1.f / fmaxf(1e-10f, depth / acc);
+    *out_acc = acc;
+  }
+  return wl;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NPART = EXACT ? 2 : 1;
+
+  const uint32_t bar_full = smem_base + kOffBars;               // [kNumSlots]
+  const uint32_t bar_empty = bar_full + kNumSlots * 8;          // [kNumSlots]
+  const uint32_t bar_aready = bar_empty + kNumSlots * 8;        // A operand of the next step is in place
+  const uint32_t bar_accfull = bar_aready + 8;                  // all MMAs of the current step completed
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+  float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNumSlots; ++i) {
+      mbar_init(bar_full + i * 8, 1);
+      mbar_init(bar_empty + i * 8, 1);
+    }
+    mbar_init(bar_aready, kRowThreads);
+    mbar_init(bar_accfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_base + kOffTmemPtr, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kBiasFloats; i += kThreads) {
+    bias_s[i] = p.bias[0][i];
+    bias_s[kBiasFloats + i] = (p.nf > 0) ? p.bias[1][i] : 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const int n_iter = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tiles_per_unit = p.tiles_c + p.tiles_f;
+
+  if (warp == 0) {
+    // ============================== weight producer ==============================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        for (int t = 0; t < tiles_per_unit; ++t) {
+          const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
+          for (int s = 0; s < kNumSteps; ++s) {
+            const StepInfo si = step_info(s);
+            for (int h = 0; h < 2; ++h) {
+              const int nh = h ? si.nh1 : si.nh0;
+              if (nh == 0) continue;
+              const uint32_t bytes = nh * 128;
+              for (int a = 0; a < si.k_atoms; ++a) {
+                const uint32_t off = kStepOff[s] + unit_offset_in_step(s, h, a);
+#pragma unroll
+                for (int part = 0; part < NPART; ++part) {
+                  const uint8_t* src = EXACT ? base + 2 * (size_t)off + part * bytes : base + off;
+                  mbar_wait(bar_empty + slot * 8, phase ^ 1);
+                  mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
+                  bulk_g2s(smem_base + kOffRing + slot * kMaxUnitBytes, src, bytes, bar_full + slot * 8);
+                  if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0, ph_a = 0;
+      const uint64_t pe_desc_hi = umma_smem_desc_sw128(smem_base + kOffPeHi);
+      const uint64_t pe_desc_lo = umma_smem_desc_sw128(smem_base + kOffPeLo);
+      for (int it = 0; it < n_iter; ++it) {
+        for (int t = 0; t < tiles_per_unit; ++t) {
+          for (int s = 0; s < kNumSteps; ++s) {
+            const StepInfo si = step_info(s);
+            mbar_wait(bar_aready, ph_a);
+            ph_a ^= 1;
+            tc_fence_after_sync();
+            for (int h = 0; h < 2; ++h) {
+              const int nh = h ? si.nh1 : si.nh0;
+              if (nh == 0) continue;
+              const uint32_t idesc = umma_idesc_f16(kTileM, nh);
+              const uint32_t d_tmem = tmem_base + kColAcc + h * 128;
+              uint32_t accum = 0;
+              for (int a = 0; a < si.k_atoms; ++a) {
+                const bool from_pe = si.pe_first && a == 0;
+                const uint32_t a_col = (a - si.pe_first) * 32;  // TMEM columns of this K atom (2 fp16 / column)
+#pragma unroll
+                for (int part = 0; part < NPART; ++part) {
+                  mbar_wait(bar_full + slot * 8, phase);
+                  tc_fence_after_sync();
+                  const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + slot * kMaxUnitBytes);
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t bd = b_desc + (uint64_t)(ks * 2);  // +32 bytes per 16-element K step
+                    if (from_pe) {
+                      umma_ss(d_tmem, pe_desc_hi + (uint64_t)(ks * 2), bd, idesc, accum);
+                      accum = 1;
+                      if (EXACT && part == 0) umma_ss(d_tmem, pe_desc_lo + (uint64_t)(ks * 2), bd, idesc, 1);
+                    } else {
+                      umma_ts(d_tmem, tmem_base + kColAhi + a_col + ks * 8, bd, idesc, accum);
+                      accum = 1;
+                      if (EXACT && part == 0) umma_ts(d_tmem, tmem_base + kColAlo + a_col + ks * 8, bd, idesc, 1);
+                    }
+                  }
+                  umma_commit(bar_empty + slot * 8);  // slot reusable once these MMAs have read it
+                  if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+                }
+              }
+            }
+            umma_commit(bar_accfull);
+          }
+        }
+      }
+    }
+  } else {
+    // ============================== row warps ==============================
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;     // tile row == TMEM lane
+    const int ew = warp - 2;           // 0..3, ray index for per-ray stages
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* pe_hi = smem + kOffPeHi;
+    uint8_t* pe_lo = smem + kOffPeLo;
+    float4* carry_raw = reinterpret_cast<float4*>(smem + kOffRaw);
+    float* carry_z = reinterpret_cast<float*>(smem + kOffZ);
+    float* scr_w = reinterpret_cast<float*>(smem + kOffW);
+    float* scr_cdf = reinterpret_cast<float*>(smem + kOffCdf);
+    float* scr_bins = reinterpret_cast<float*>(smem + kOffBins);
+    float* scr_sort = reinterpret_cast<float*>(smem + kOffSort);
+    float* dirbias = reinterpret_cast<float*>(smem + kOffDirBias);
+    RayP* rayp = reinterpret_cast<RayP*>(smem + kOffRay);
+    const int R = p.rays_per_unit;
+    const bool has_bg = p.bg != nullptr;
+    uint32_t ph_acc = 0;
+
+    for (int it = 0; it < n_iter; ++it) {
+      const int unit = blockIdx.x + it * gridDim.x;
+      // ---- per-ray constants
+      if (row < R) {
+        RayP& rp = rayp[row];
+        const int g = unit * R + row;
+        rp.valid = g < p.n_rays;
+        rp.gidx = g;
+        if (rp.valid) {
+          float o0, o1, o2, d0, d1, d2;
+          if (p.o) {
+            o0 = p.o[3 * g]; o1 = p.o[3 * g + 1]; o2 = p.o[3 * g + 2];
+            d0 = p.d[3 * g]; d1 = p.d[3 * g + 1]; d2 = p.d[3 * g + 2];
+          } else {  // get_ray_bundle (nerf_helpers.py:111-122), same operation order in FP32
+            const int pj = p.row_begin + g / p.width, pi = g % p.width;
+            const float cx = __fdiv_rn(__fsub_rn((float)pi, p.wcx), p.fx);
+            const float cy = -__fdiv_rn(__fsub_rn((float)pj, p.hcy), p.fy);
+            d0 = __fadd_rn(__fadd_rn(__fmul_rn(cx, p.pose[0]), __fmul_rn(cy, p.pose[1])), __fmul_rn(-1.f, p.pose[2]));
+            d1 = __fadd_rn(__fadd_rn(__fmul_rn(cx, p.pose[4]), __fmul_rn(cy, p.pose[5])), __fmul_rn(-1.f, p.pose[6]));
+            d2 = __fadd_rn(__fadd_rn(__fmul_rn(cx, p.pose[8]), __fmul_rn(cy, p.pose[9])), __fmul_rn(-1.f, p.pose[10]));
+            o0 = p.pose[3]; o1 = p.pose[7]; o2 = p.pose[11];
+          }
+          rp.o[0] = o0; rp.o[1] = o1; rp.o[2] = o2;
+          rp.d[0] = d0; rp.d[1] = d1; rp.d[2] = d2;
+          rp.dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+          if (has_bg) { rp.bg[0] = p.bg[3 * g]; rp.bg[1] = p.bg[3 * g + 1]; rp.bg[2] = p.bg[3 * g + 2]; }
+          // direction encoder input is (d_z, near, far): run_network reads ray_batch[..., -3:] (train_utils.py:14)
+          const float v[3] = {p.dir_z ? p.dir_z[g] : d2, p.near_, p.far_};
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float sn, cs;
+              sincosf(v[c] * (float)(1 << f), &sn, &cs);
+              rp.ped[6 * f + c] = sn;
+              rp.ped[6 * f + 3 + c] = cs;
+            }
+          }
+        } else {
+          for (int k = 0; k < 3; ++k) { rp.o[k] = 0.f; rp.d[k] = 0.f; rp.bg[k] = 0.f; }
+          rp.dnorm = 0.f;
+          for (int k = 0; k < 24; ++k) rp.ped[k] = 0.f;
+        }
+      }
+      named_bar_sync(kRowBarrier, kRowThreads);
+
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && p.nf == 0) break;
+        const int S = pass ? p.s_fine : p.nc;
+        const int rows = R * S;
+        const int n_tiles = pass ? p.tiles_f : p.tiles_c;
+        const float* bias_n = bias_s + pass * kBiasFloats;
+
+        // per-ray additive term of layers_dir.0: W[:, 256:280] . PE_dir  (one output feature per thread)
+        {
+          const float* wt = p.wd0b_t[pass];
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+          for (int j = 0; j < kDimDir; ++j) {
+            const float w = wt[j * 128 + row];
+            acc0 = fmaf(w, rayp[0].ped[j], acc0);
+            if (R > 1) acc1 = fmaf(w, rayp[1].ped[j], acc1);
+          }
+          dirbias[row] = acc0;
+          dirbias[128 + row] = acc1;
+        }
+
+        for (int t = 0; t < n_tiles; ++t) {
+          const int prow = t * 128 + row;  // pass-local row
+          const bool live = prow < rows;
+          const int r = live ? prow / S : 0;
+          const int i = live ? prow - r * S : 0;
+          const RayP& rp = rayp[r];
+          // ---- sample depth
+          float z = 0.f;
+          if (live) {
+            if (pass == 0) {
+              const float tc = p.t_coarse[i];
+              z = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tc)), __fmul_rn(p.far_, tc));
+              if (p.perturb) {  // stratified jitter (train_utils.py:69-76)
+                float lower = z, upper = z;
+                if (i > 0) {
+                  const float tp = p.t_coarse[i - 1];
+                  const float zp = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tp)), __fmul_rn(p.far_, tp));
+                  lower = __fmul_rn(0.5f, __fadd_rn(z, zp));
+                }
+                if (i < S - 1) {
+                  const float tn = p.t_coarse[i + 1];
+                  const float zn = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tn)), __fmul_rn(p.far_, tn));
+                  upper = __fmul_rn(0.5f, __fadd_rn(zn, z));
+                }
+                const float tr = rp.valid ? p.t_rand[(size_t)rp.gidx * p.nc + i] : 0.f;
+                z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
+              }
+              carry_z[prow] = z;
+            } else {
+              z = carry_z[prow];
+            }
+          }
+          // ---- positional encoding of o + d*z (63 lanes + 1 zero pad), FP16 (hi[,lo]) into the PE buffer
+          {
+            float f[64];
+            const float px = __fadd_rn(rp.o[0], __fmul_rn(rp.d[0], z));
+            const float py = __fadd_rn(rp.o[1], __fmul_rn(rp.d[1], z));
+            const float pz = __fadd_rn(rp.o[2], __fmul_rn(rp.d[2], z));
+            f[0] = px; f[1] = py; f[2] = pz;
+#pragma unroll
+            for (int fr = 0; fr < 10; ++fr) {
+              const float sc = (float)(1 << fr);
+              pe_sincos<EXACT>(px * sc, f[3 + 6 * fr + 0], f[3 + 6 * fr + 3]);
+              pe_sincos<EXACT>(py * sc, f[3 + 6 * fr + 1], f[3 + 6 * fr + 4]);
+              pe_sincos<EXACT>(pz * sc, f[3 + 6 * fr + 2], f[3 + 6 * fr + 5]);
+            }
+            f[63] = 0.f;
+            store_pe_row<EXACT>(pe_hi, pe_lo, row, f);
+            if (p.dbg_act && p.dbg_act_step == -1 && unit == 0 && pass == 0 && t == 0) {
+#pragma unroll
+              for (int k = 0; k < 64; ++k) p.dbg_act[row * 256 + k] = f[k];
+            }
+          }
+          fence_proxy_async_smem();  // make the generic-proxy PE stores visible to the tensor core
+          if (t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias / carry_z of other threads
+          mbar_arrive(bar_aready);
+
+          float sigma_raw = 0.f;
+          for (int s = 0; s < kNumSteps; ++s) {
+            mbar_wait(bar_accfull, ph_acc);
+            ph_acc ^= 1;
+            tc_fence_after_sync();
+            float* dump = (p.dbg_act && p.dbg_act_step == s && unit == 0 && pass == 0 && t == 0) ? p.dbg_act + row * 256 : nullptr;
+            const StepInfo si = step_info(s);
+            if (s <= 5) {
+#pragma unroll 1
+              for (int c = 0; c < 8; ++c)
+                epi_chunk<EXACT>(t_lane + kColAcc + c * 32, t_lane + kColAhi + c * 16, t_lane + kColAlo + c * 16,
+                                 bias_n + si.bias_off + c * 32, nullptr, dump ? dump + c * 32 : nullptr);
+            } else if (s <= 8) {
+              const float* extra = (s == 6) ? dirbias + r * 128 : nullptr;
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c)
+                epi_chunk<EXACT>(t_lane + kColAcc + c * 32, t_lane + kColAhi + c * 16, t_lane + kColAlo + c * 16,
+                                 bias_n + si.bias_off + c * 32, extra ? extra + c * 32 : nullptr, dump ? dump + c * 32 : nullptr);
+              if (s == 6) {
+                uint32_t v[4];
+                tmem_ld4(t_lane + kColAcc + 128, v);
+                tmem_wait_ld();
+                sigma_raw = __uint_as_float(v[0]) + bias_n[si.bias_off + 128];
+              }
+            } else {
+              uint32_t v[4];
+              tmem_ld4(t_lane + kColAcc, v);
+              tmem_wait_ld();
+              const float* b = bias_n + si.bias_off;
+              if (live) carry_raw[prow] = make_float4(__uint_as_float(v[0]) + b[0], __uint_as_float(v[1]) + b[1],
+                                                       __uint_as_float(v[2]) + b[2], sigma_raw);
+            }
+            if (s < kNumSteps - 1) {
+              tmem_wait_st();
+              tc_fence_before_sync();
+              mbar_arrive(bar_aready);
+            }
+          }
+        }  // tiles
+        named_bar_sync(kRowBarrier, kRowThreads);
+
+        // ---- debug dumps of the per-sample tensors
+        {
+          float* dz = pass ? p.dbg_z_f : p.dbg_z_c;
+          float* dr = pass ? p.dbg_raw_f : p.dbg_raw_c;
+          if (dz || dr) {
+            for (int k = row; k < rows; k += kRowThreads) {
+              const int rr = k / S;
+              if (!rayp[rr].valid) continue;
+              const size_t gi = (size_t)rayp[rr].gidx * S + (k - rr * S);
+              if (dz) dz[gi] = carry_z[k];
+              if (dr) reinterpret_cast<float4*>(dr)[gi] = carry_raw[k];
+            }
+          }
+        }
+
+        // ---- compositing: warp `ew` renders ray `ew`
+        if (ew < R && rayp[ew].valid) {
+          const RayP& rp = rayp[ew];
+          const int g = rp.gidx;
+          const float* nz = nullptr;
+          if (p.noise_std > 0.f) nz = (pass ? p.noise_f : p.noise_c) + (size_t)g * S;
+          float* o_rgb = pass ? p.rgb_f : p.rgb_c;
+          float* o_disp = pass ? p.disp_f : p.disp_c;
+          float* o_acc = pass ? p.acc_f : p.acc_c;
+          const float wl = composite_ray(carry_raw + ew * S, carry_z + ew * S, scr_w + ew * S, S, rp, has_bg, p.noise_std, nz,
+                                         p.white_bkgd != 0, o_rgb ? o_rgb + 3 * (size_t)g : nullptr,
+                                         o_disp ? o_disp + g : nullptr, o_acc ? o_acc + g : nullptr, lane);
+          const bool last_pass = (pass == 1) || (p.nf == 0);
+          if (last_pass && lane == 0 && p.w_last) p.w_last[g] = wl;
+        }
+        if (pass == 1 || p.nf == 0) {
+          named_bar_sync(kRowBarrier, kRowThreads);  // carry buffers are reused by the next unit
+          continue;
+        }
+
+        // ---- inverse-CDF resampling (nerf_helpers.py:344-387) on weights[1:-1] over the mid-point bins
+        __syncwarp();
+        const int nb = p.nc - 1;   // bins / cdf entries
+        const int nw = p.nc - 2;   // interior weights
+        if (ew < R) {
+          const float* w = scr_w + ew * p.nc;
+          const float* zc = carry_z + ew * p.nc;
+          float* cdf = scr_cdf + ew * p.nc;
+          float* bins = scr_bins + ew * p.nc;
+          for (int k = lane; k < nb; k += 32) bins[k] = __fmul_rn(0.5f, __fadd_rn(zc[k + 1], zc[k]));
+          const int per = (nw + 31) >> 5;
+          const int k0 = lane * per;
+          float part = 0.f;
+          for (int j = 0; j < per; ++j)
+            if (k0 + j < nw) part += __fadd_rn(w[k0 + j + 1], 1e-5f);
+          const float total = warp_sum(part);
+          float psum = 0.f;
+          for (int j = 0; j < per; ++j)
+            if (k0 + j < nw) psum += __fdiv_rn(__fadd_rn(w[k0 + j + 1], 1e-5f), total);
+          float incl = psum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float tt = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += tt;
+          }
+          float run = incl - psum;  // exclusive prefix of this lane's block
+          if (lane == 0) cdf[0] = 0.f;
+          for (int j = 0; j < per; ++j)
+            if (k0 + j < nw) {
+              run += __fdiv_rn(__fadd_rn(w[k0 + j + 1], 1e-5f), total);
+              cdf[k0 + j + 1] = run;
+            }
+        }
+        named_bar_sync(kRowBarrier, kRowThreads);
+        int P = 1;
+        while (P < p.s_fine) P <<= 1;
+        for (int k = row; k < R * P; k += kRowThreads) {
+          const int rr = k / P, i = k - rr * P;
+          float val = CUDART_INF_F;
+          if (i < p.nc) {
+            val = carry_z[rr * p.nc + i];
+          } else if (i < p.s_fine) {
+            const int j = i - p.nc;
+            const float* cdf = scr_cdf + rr * p.nc;
+            const float* bins = scr_bins + rr * p.nc;
+            const float u = p.perturb ? (rayp[rr].valid ? p.u_rand[(size_t)rayp[rr].gidx * p.nf + j] : 0.f) : p.u_fine[j];
+            int lo = 0, hi = nb;  // searchsorted(..., right=True): number of cdf entries <= u
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+            }
+            const int below = max(0, lo - 1), above = min(nb - 1, lo);
+            const float cb = cdf[below], ca = cdf[above];
+            float den = __fsub_rn(ca, cb);
+            if (den < 1e-5f) den = 1.f;
+            const float tt = __fdiv_rn(__fsub_rn(u, cb), den);
+            val = __fadd_rn(bins[below], __fmul_rn(tt, __fsub_rn(bins[above], bins[below])));
+          }
+          scr_sort[k] = val;
+        }
+        named_bar_sync(kRowBarrier, kRowThreads);
+        // ---- torch.sort(cat(z, z_samples)) per ray: bitonic network over P (padded with +inf)
+        for (int kk = 2; kk <= P; kk <<= 1) {
+          for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int c = row; c < R * (P >> 1); c += kRowThreads) {
+              const int rr = c / (P >> 1), tq = c - rr * (P >> 1);
+              const int i = 2 * tq - (tq & (j - 1));
+              const int l = i + j;
+              float* a = scr_sort + rr * P;
+              const float x = a[i], y = a[l];
+              const bool up = (i & kk) == 0;
+              if ((x > y) == up) { a[i] = y; a[l] = x; }
+            }
+            named_bar_sync(kRowBarrier, kRowThreads);
+          }
+        }
+        for (int k = row; k < R * p.s_fine; k += kRowThreads) {
+          const int rr = k / p.s_fine, i = k - rr * p.s_fine;
+          carry_z[k] = scr_sort[rr * P + i];
+        }
+        named_bar_sync(kRowBarrier, kRowThreads);
+      }  // pass
+    }    // units
+    tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+cudaError_t render_kernel_setup() {
+  cudaError_t e = cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+}
+
+cudaError_t launch_render(const RenderParams& p, int precision, int num_sms, cudaStream_t st, long long* launches) {
+  const int grid = p.n_units < num_sms ? p.n_units : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  if (precision == 1)
+    render_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
+  else
+    render_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(p);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace nfb

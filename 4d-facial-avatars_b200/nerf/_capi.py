@@ -1,0 +1,89 @@
+"""ctypes binding of include/nfb.h (lib/libnfb.so).  The library is REQUIRED: importing this module
+raises if it is missing — there is no PyTorch or CPU fallback for the render path."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnfb.so")
+
+NFB_OK = 0
+NFB_NET_COARSE, NFB_NET_FINE = 0, 1
+NFB_PREC_FAST, NFB_PREC_EXACT = 0, 1
+
+EXPORTS = ["nfb_version", "nfb_strerror", "nfb_last_cuda_error", "nfb_create", "nfb_destroy", "nfb_load_weights",
+           "nfb_set_frame", "nfb_render_forward", "nfb_render_backward", "nfb_render_frame_host", "nfb_launch_count",
+           "nfb_host_linspace"]
+
+
+class NfbModelDims(C.Structure):
+    _fields_ = [("num_encoding_fn_xyz", C.c_int32), ("num_encoding_fn_dir", C.c_int32), ("include_input_xyz", C.c_int32),
+                ("include_input_dir", C.c_int32), ("dim_expression", C.c_int32), ("dim_latent", C.c_int32)]
+
+
+class NfbRays(C.Structure):
+    _fields_ = [("o", C.c_void_p), ("d", C.c_void_p), ("n_rays", C.c_int32), ("pose", C.c_float * 12),
+                ("intrinsics", C.c_double * 4), ("height", C.c_int32), ("width", C.c_int32), ("row_begin", C.c_int32),
+                ("near_", C.c_float), ("far_", C.c_float), ("dir_z", C.c_void_p), ("background", C.c_void_p)]
+
+
+class NfbSampling(C.Structure):
+    _fields_ = [("num_coarse", C.c_int32), ("num_fine", C.c_int32), ("perturb", C.c_int32), ("noise_std", C.c_float),
+                ("white_background", C.c_int32), ("lindisp", C.c_int32), ("precision", C.c_int32),
+                ("t_coarse", C.c_void_p), ("u_fine", C.c_void_p)]
+
+
+class NfbNoise(C.Structure):
+    _fields_ = [("t_rand", C.c_void_p), ("sigma_noise_c", C.c_void_p), ("u", C.c_void_p), ("sigma_noise_f", C.c_void_p)]
+
+
+class NfbOutputs(C.Structure):
+    _fields_ = [("rgb_coarse", C.c_void_p), ("disp_coarse", C.c_void_p), ("acc_coarse", C.c_void_p),
+                ("rgb_fine", C.c_void_p), ("disp_fine", C.c_void_p), ("acc_fine", C.c_void_p), ("w_last", C.c_void_p)]
+
+
+class NfbDebug(C.Structure):
+    _fields_ = [("z_coarse", C.c_void_p), ("raw_coarse", C.c_void_p), ("z_fine", C.c_void_p), ("raw_fine", C.c_void_p),
+                ("act_dump", C.c_void_p), ("act_step", C.c_int32)]
+
+
+class NfbOutGrads(C.Structure):
+    _fields_ = [("d_rgb_coarse", C.c_void_p), ("d_rgb_fine", C.c_void_p)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not found: build it with `python 4d-facial-avatars_b200/build.py` "
+                          "(the render path has no fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.nfb_version.restype = C.c_int
+    lib.nfb_strerror.restype = C.c_char_p
+    lib.nfb_strerror.argtypes = [C.c_int]
+    lib.nfb_last_cuda_error.restype = C.c_char_p
+    lib.nfb_create.argtypes = [C.POINTER(NfbModelDims), C.c_int, C.POINTER(C.c_void_p)]
+    lib.nfb_destroy.argtypes = [C.c_void_p]
+    lib.nfb_load_weights.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.nfb_set_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.nfb_render_forward.argtypes = [C.c_void_p, C.POINTER(NfbRays), C.POINTER(NfbSampling), C.POINTER(NfbNoise),
+                                       C.POINTER(NfbOutputs), C.POINTER(NfbDebug), C.c_void_p]
+    lib.nfb_render_frame_host.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(NfbSampling), C.c_void_p, C.c_void_p]
+    lib.nfb_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+    lib.nfb_host_linspace.argtypes = [C.POINTER(C.c_float), C.c_int]
+    if hasattr(lib, "nfb_render_backward"):
+        lib.nfb_render_backward.argtypes = [C.c_void_p, C.POINTER(NfbRays), C.POINTER(NfbSampling), C.POINTER(NfbNoise),
+                                            C.POINTER(NfbDebug), C.POINTER(NfbOutGrads), C.c_void_p, C.c_void_p]
+    for fn in ("nfb_create", "nfb_destroy", "nfb_load_weights", "nfb_set_frame", "nfb_render_forward",
+               "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace"):
+        getattr(lib, fn).restype = C.c_int
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what=""):
+    if rc != NFB_OK:
+        msg = lib.nfb_strerror(rc).decode()
+        detail = lib.nfb_last_cuda_error().decode()
+        raise RuntimeError(f"nfb {what}: {msg}" + (f" [{detail}]" if detail and rc == 3 else ""))

@@ -1,0 +1,184 @@
+"""Host-side engine: owns NfbHandle objects, keeps the packed weight streams in sync with the caller's
+FP32 nn.Parameters, and launches the fused render kernel on torch's current CUDA stream.
+
+torch is used here only for device memory, streams and (in the trainer) torch.distributed."""
+import ctypes as C
+import os
+import weakref
+
+import torch
+
+from . import _capi as capi
+
+PARAM_ORDER = ([f"layers_xyz.{i}.{k}" for i in range(6) for k in ("weight", "bias")]
+               + ["fc_feat.weight", "fc_feat.bias", "fc_alpha.weight", "fc_alpha.bias"]
+               + [f"layers_dir.{i}.{k}" for i in range(4) for k in ("weight", "bias")]
+               + ["fc_rgb.weight", "fc_rgb.bias"])
+
+_precision = os.environ.get("NFB_PRECISION", "fast")
+
+
+def set_precision(mode: str):
+    """'fast' = FP16 operands / FP32 accumulate; 'exact' = 3-pass FP16 hi/lo split (see include/nfb.h)."""
+    global _precision
+    if mode not in ("fast", "exact"):
+        raise ValueError("precision must be 'fast' or 'exact'")
+    _precision = mode
+
+
+def get_precision() -> str:
+    return _precision
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class Renderer:
+    """One NfbHandle on one CUDA device plus the bookkeeping that decides when weights must be re-packed."""
+
+    def __init__(self, device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("the nfb render path runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.device = device
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        dims = capi.NfbModelDims(10, 4, 1, 0, 76, 32)
+        h = C.c_void_p()
+        capi.check(capi.lib.nfb_create(C.byref(dims), idx, C.byref(h)), "create")
+        self._h = h
+        self._lin = {}
+        self._versions = [None, None]
+        self._keep = [None, None]  # contiguous FP32 copies handed to the pack kernels
+        weakref.finalize(self, capi.lib.nfb_destroy, h)
+
+    @staticmethod
+    def _fingerprint(model):
+        sd = dict(model.named_parameters())
+        return tuple((sd[k].data_ptr(), sd[k]._version) for k in PARAM_ORDER)
+
+    def sync_weights(self, model_coarse, model_fine):
+        for which, model in ((capi.NFB_NET_COARSE, model_coarse), (capi.NFB_NET_FINE, model_fine)):
+            if model is None:
+                continue
+            fp = self._fingerprint(model)
+            if fp == self._versions[which]:
+                continue
+            sd = dict(model.named_parameters())
+            tensors = [_f32c(sd[k], self.device) for k in PARAM_ORDER]
+            arr = (C.c_void_p * 26)(*[t.data_ptr() for t in tensors])
+            capi.check(capi.lib.nfb_load_weights(self._h, which, arr, _stream()), "load_weights")
+            self._keep[which] = tensors
+            self._versions[which] = fp
+
+    def linspace(self, n):
+        """torch.linspace(0, 1, n) evaluated by ATen's CPU kernel (whose vectorised halves are not the scalar
+        formula of nfb_host_linspace) and cached on the device, so depths match the CPU reference bit for bit."""
+        t = self._lin.get(n)
+        if t is None:
+            t = self._lin[n] = torch.linspace(0.0, 1.0, n, dtype=torch.float32).to(self.device)
+        return t
+
+    def set_frame(self, expressions, latent_code):
+        e = _f32c(expressions, self.device).reshape(-1)
+        l = _f32c(latent_code, self.device).reshape(-1)
+        if e.numel() != 76 or l.numel() != 32:
+            raise ValueError("expressions must have 76 and latent_code 32 elements")
+        capi.check(capi.lib.nfb_set_frame(self._h, _ptr(e), _ptr(l), _stream()), "set_frame")
+        self._frame = (e, l)
+
+    def launch_count(self) -> int:
+        n = C.c_longlong()
+        capi.check(capi.lib.nfb_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def render(self, ro, rd, near, far, num_coarse, num_fine, perturb=False, noise_std=0.0, white_bkgd=False,
+               background=None, dir_z=None, noise=None, precision=None, debug=False, act_step=None):
+        """ro, rd: [N,3] CUDA FP32.  noise: dict with t_rand, n_c, u, n_f (any may be None).  Returns a dict
+        with the seven outputs (+ per-sample dumps when debug)."""
+        dev = self.device
+        ro, rd = _f32c(ro, dev), _f32c(rd, dev)
+        n = ro.shape[0]
+        has_fine = num_fine > 0
+        out = {k: torch.empty((n, 3) if k.startswith("rgb") else (n,), device=dev, dtype=torch.float32)
+               for k in ("rgb_coarse", "disp_coarse", "acc_coarse", "w_last")}
+        if has_fine:
+            out.update({k: torch.empty((n, 3) if k.startswith("rgb") else (n,), device=dev, dtype=torch.float32)
+                        for k in ("rgb_fine", "disp_fine", "acc_fine")})
+        rays = capi.NfbRays()
+        rays.o, rays.d, rays.n_rays = ro.data_ptr(), rd.data_ptr(), n
+        rays.near_, rays.far_ = float(near), float(far)
+        keep = [ro, rd]
+        if background is not None:
+            bg = _f32c(background, dev).reshape(n, 3)
+            rays.background = bg.data_ptr()
+            keep.append(bg)
+        if dir_z is not None:
+            dz = _f32c(dir_z, dev).reshape(n)
+            rays.dir_z = dz.data_ptr()
+            keep.append(dz)
+        prec = precision or _precision
+        sm = capi.NfbSampling(num_coarse, num_fine, int(bool(perturb)), float(noise_std), int(bool(white_bkgd)), 0,
+                              capi.NFB_PREC_EXACT if prec == "exact" else capi.NFB_PREC_FAST,
+                              self.linspace(num_coarse).data_ptr(),
+                              self.linspace(num_fine).data_ptr() if has_fine else None)
+        nz = capi.NfbNoise()
+        if noise:
+            for field, key in (("t_rand", "t_rand"), ("sigma_noise_c", "n_c"), ("u", "u"), ("sigma_noise_f", "n_f")):
+                t = noise.get(key)
+                if t is not None:
+                    t = _f32c(t, dev)
+                    keep.append(t)
+                    setattr(nz, field, t.data_ptr())
+        o = capi.NfbOutputs(out["rgb_coarse"].data_ptr(), out["disp_coarse"].data_ptr(), out["acc_coarse"].data_ptr(),
+                            out["rgb_fine"].data_ptr() if has_fine else None,
+                            out["disp_fine"].data_ptr() if has_fine else None,
+                            out["acc_fine"].data_ptr() if has_fine else None, out["w_last"].data_ptr())
+        dbg = None
+        if debug or act_step is not None:
+            s = num_coarse + num_fine
+            out["z_coarse"] = torch.zeros((n, num_coarse), device=dev)
+            out["raw_coarse"] = torch.zeros((n, num_coarse, 4), device=dev)
+            dbg = capi.NfbDebug(out["z_coarse"].data_ptr(), out["raw_coarse"].data_ptr(), None, None, None, 0)
+            if has_fine:
+                out["z_fine"] = torch.zeros((n, s), device=dev)
+                out["raw_fine"] = torch.zeros((n, s, 4), device=dev)
+                dbg.z_fine, dbg.raw_fine = out["z_fine"].data_ptr(), out["raw_fine"].data_ptr()
+            if act_step is not None:
+                out["act"] = torch.zeros((128, 256), device=dev)
+                dbg.act_dump, dbg.act_step = out["act"].data_ptr(), int(act_step)
+        capi.check(capi.lib.nfb_render_forward(self._h, C.byref(rays), C.byref(sm), C.byref(nz) if noise else None,
+                                               C.byref(o), C.byref(dbg) if dbg is not None else None, _stream()),
+                   "render_forward")
+        out["_keep"] = keep  # inputs must outlive the asynchronous launch
+        return out
+
+    def render_frame_host(self, pose, intrinsics, height, width, row_begin, rows, near, far, expr_host, latent_host,
+                          bg_host, num_coarse, num_fine, out_host, precision=None, white_bkgd=False):
+        """Host-buffer end-to-end call (bench e2e leg).  All tensors are CPU (ideally pinned) FP32."""
+        prec = precision or _precision
+        sm = capi.NfbSampling(num_coarse, num_fine, 0, 0.0, int(bool(white_bkgd)), 0,
+                              capi.NFB_PREC_EXACT if prec == "exact" else capi.NFB_PREC_FAST, None, None)
+        pose_a = (C.c_float * 12)(*[float(v) for v in pose.reshape(-1)[:12]])
+        intr_a = (C.c_double * 4)(*[float(v) for v in intrinsics])
+        capi.check(capi.lib.nfb_render_frame_host(self._h, pose_a, intr_a, height, width, row_begin, rows, float(near),
+                                                  float(far), _ptr(expr_host), _ptr(latent_host), _ptr(bg_host),
+                                                  C.byref(sm), _ptr(out_host), _stream()), "render_frame_host")
+
+
+_renderers = {}
+
+
+def renderer_for(device: torch.device) -> Renderer:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    r = _renderers.get(key)
+    if r is None:
+        r = _renderers[key] = Renderer(torch.device("cuda", key[1]))
+    return r

@@ -1,0 +1,176 @@
+/* nfb.h — C ABI of the B200-native NeRFace render path ("nfb" = NeRFace on Blackwell).
+ *
+ * This is the drop-in boundary for ONE hot path of gafniguy/4D-Facial-Avatars: the per-ray render
+ * loop reached through nerface_code/nerf-pytorch/nerf/train_utils.py (run_one_iter_of_nerf :165-290,
+ * predict_and_render_radiance :36-162, run_network :9-33), nerf_helpers.py (get_ray_bundle :68-123,
+ * positional_encoding :195-239, sample_pdf_2 :344-387, cumprod_exclusive :44-65),
+ * volume_rendering_utils.py (volume_render_radiance_field :7-75) and models.py
+ * (ConditionalBlendshapePaperNeRFModel :189-261).  The reference has no FFI (it is pure PyTorch);
+ * the Python package 4d-facial-avatars_b200/nerf binds these entry points with ctypes and keeps the
+ * reference's call surface.  See INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes, no torch types.  Every entry returns an int status
+ * (0 = NFB_OK) and never throws; nfb_strerror() maps it to text.  All device pointers are FP32,
+ * row-major, 16-byte aligned, on the device the handle was created for.  Calls are asynchronous on
+ * the given cudaStream_t (passed as void*) unless stated otherwise; no entry synchronises the device
+ * except nfb_render_frame_host and nfb_selftest.
+ */
+#ifndef NFB_H_
+#define NFB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFB_VERSION 100
+
+typedef struct NfbHandle NfbHandle;
+
+enum {
+  NFB_OK = 0,
+  NFB_ERR_INVALID = 1,     /* bad argument (null pointer, negative size, ...) */
+  NFB_ERR_UNSUPPORTED = 2, /* configuration outside what the kernel implements */
+  NFB_ERR_CUDA = 3,        /* a CUDA runtime call failed; see nfb_last_cuda_error() */
+  NFB_ERR_STATE = 4,       /* call order violated (weights or frame not set) */
+  NFB_ERR_ARCH = 5         /* device is not sm_100 */
+};
+
+/* Which of the two networks (models.coarse / models.fine in the reference YAML). */
+enum { NFB_NET_COARSE = 0, NFB_NET_FINE = 1 };
+
+/* Arithmetic used by the tensor-core MLP.
+ *   NFB_PREC_FAST  : FP16 operands (round-to-nearest), FP32 accumulate, one tcgen05 pass.
+ *   NFB_PREC_EXACT : every operand split x = hi + lo in FP16; hi*hi + hi*lo + lo*hi, FP32
+ *                    accumulate (3 tcgen05 passes, ~2^-21 relative operand error). */
+enum { NFB_PREC_FAST = 0, NFB_PREC_EXACT = 1 };
+
+/* Encoder / conditioning dimensions; mirrors the constructor arguments of
+ * ConditionalBlendshapePaperNeRFModel (models.py:193-206).  Only the shipped paper configuration
+ * (10, 4, include_input_xyz=1, include_input_dir=0, 76, 32) is implemented. */
+typedef struct {
+  int32_t num_encoding_fn_xyz;
+  int32_t num_encoding_fn_dir;
+  int32_t include_input_xyz;
+  int32_t include_input_dir;
+  int32_t dim_expression;
+  int32_t dim_latent;
+} NfbModelDims;
+
+/* Rays of one call.  Either explicit rays (o and d non-null; what run_one_iter_of_nerf receives,
+ * train_utils.py:171-172) or in-kernel generation from a camera (o == d == NULL; replaces
+ * get_ray_bundle, nerf_helpers.py:68-123, for image rows [row_begin, row_begin + n_rays / width)). */
+typedef struct {
+  const float* o;          /* [n_rays,3] device, or NULL */
+  const float* d;          /* [n_rays,3] device, unnormalised, or NULL */
+  int32_t n_rays;
+  float pose[12];          /* row-major 3x4 camera-to-world (used when o == NULL) */
+  double intrinsics[4];    /* fx, fy, cx, cy with cx, cy relative in [0,1]; FP64 like the reference's numpy
+                              array (load_flame.py:114-118), rounded to FP32 where torch would */
+  int32_t height, width, row_begin;
+  float near_, far_;       /* options.dataset.near / far (train_utils.py:210-211) */
+  const float* dir_z;      /* optional [n_rays]: overrides d_z as the first input of the direction
+                              encoder (ray_directions_ablation path, train_utils.py:81-82); NULL = d_z */
+  const float* background; /* optional [n_rays,3] background_prior (train_utils.py:95-96) or NULL */
+} NfbRays;
+
+/* options.nerf.<mode>.* (train_utils.py:56-69,108-122). */
+typedef struct {
+  int32_t num_coarse, num_fine;
+  int32_t perturb;          /* stratified coarse samples; also makes the fine resampling stochastic */
+  float noise_std;          /* radiance_field_noise_std */
+  int32_t white_background;
+  int32_t lindisp;          /* must be 0 (all shipped YAMLs) */
+  int32_t precision;        /* NFB_PREC_* */
+  const float* t_coarse;    /* optional device [num_coarse] = torch.linspace(0,1,num_coarse); NULL: computed */
+  const float* u_fine;      /* optional device [num_fine]  = torch.linspace(0,1,num_fine);  NULL: computed */
+} NfbSampling;
+
+/* Explicit noise, in the reference's draw order per ray chunk.  Required members:
+ * t_rand and u when perturb != 0; sigma_noise_* when noise_std > 0.  All device pointers. */
+typedef struct {
+  const float* t_rand;        /* [n_rays, num_coarse] uniform [0,1) */
+  const float* sigma_noise_c; /* [n_rays, num_coarse] standard normal */
+  const float* u;             /* [n_rays, num_fine] uniform [0,1) */
+  const float* sigma_noise_f; /* [n_rays, num_coarse+num_fine] standard normal */
+} NfbNoise;
+
+/* The 7-tuple of predict_and_render_radiance (train_utils.py:162).  Fine members may be NULL when
+ * num_fine == 0; then w_last receives the coarse pass's last weight. */
+typedef struct {
+  float* rgb_coarse;  /* [n_rays,3] */
+  float* disp_coarse; /* [n_rays] */
+  float* acc_coarse;  /* [n_rays] */
+  float* rgb_fine;    /* [n_rays,3] */
+  float* disp_fine;   /* [n_rays] */
+  float* acc_fine;    /* [n_rays] */
+  float* w_last;      /* [n_rays] weights[:, -1] of the last pass */
+} NfbOutputs;
+
+/* Optional per-sample dumps (tests, and the tensors a backward pass needs).  Any member may be NULL. */
+typedef struct {
+  float* z_coarse;   /* [n_rays, num_coarse] */
+  float* raw_coarse; /* [n_rays, num_coarse, 4] MLP output (rgb raw, sigma raw), before the bg overwrite */
+  float* z_fine;     /* [n_rays, num_coarse+num_fine] sorted */
+  float* raw_fine;   /* [n_rays, num_coarse+num_fine, 4] */
+  /* Layer probe: post-activation FP32 values the epilogue of tensor-core step `act_step` (0..8, see
+   * nfb_layout.h; -1 = the 64-lane positional encoding) produced for the first 128 coarse rows
+   * (rays 0.., samples in order).  [128, 256] floats; columns beyond the step's width are untouched. */
+  float* act_dump;
+  int32_t act_step;
+} NfbDebug;
+
+int nfb_version(void);
+const char* nfb_strerror(int status);
+/* Text of the last CUDA error seen by this thread's calls (empty string if none). */
+const char* nfb_last_cuda_error(void);
+
+/* Create / destroy a renderer bound to one CUDA device.  Allocates the packed-weight streams,
+ * per-frame constant buffers and per-CTA scratch (a few MB). */
+int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out);
+int nfb_destroy(NfbHandle* h);
+
+/* Load one network.  `params` holds 26 DEVICE pointers in the reference's state_dict order
+ * (models.py:218-233): layers_xyz.{0..5}.{weight,bias}, fc_feat.{weight,bias}, fc_alpha.{weight,bias},
+ * layers_dir.{0..3}.{weight,bias}, fc_rgb.{weight,bias} — weights row-major (out,in).  Folds fc_feat
+ * into fc_alpha / layers_dir.0 (exact algebra, FP64), splits to FP16 hi/lo and writes the
+ * shared-memory-image weight streams the kernel's bulk copies read.  layers_dir.3 is ignored, as in
+ * the reference's forward (models.py:257). */
+int nfb_load_weights(NfbHandle* h, int which, const float* const params[26], void* stream);
+
+/* Per-frame conditioning: expression[76] (divided by 3 inside, models.py:241) and latent[32], both
+ * DEVICE pointers.  Folds W0[:,63:171]·c and W3[:,63:171]·c into the layer-0 / layer-3 biases of both
+ * loaded networks. */
+int nfb_set_frame(NfbHandle* h, const float* expression, const float* latent, void* stream);
+
+/* The hot path: coarse sampling -> encode -> coarse MLP -> composite -> inverse-CDF resample -> sort
+ * -> encode -> fine MLP -> composite, one persistent sm_100a kernel launch. */
+int nfb_render_forward(NfbHandle* h, const NfbRays* rays, const NfbSampling* sampling,
+                       const NfbNoise* noise /* nullable */, const NfbOutputs* out,
+                       const NfbDebug* dbg /* nullable */, void* stream);
+
+/* End-to-end convenience for callers with HOST buffers (bench.py's e2e leg, C/C++ users): copies
+ * expression/latent/background to the device, renders image rows [row_begin,row_begin+rows) of a
+ * height x width frame with in-kernel ray generation, and copies the outputs back.  Host pointers
+ * should be pinned for full copy speed.  Output layout: out_host = rgb_c[n,3] | disp_c[n] | acc_c[n] |
+ * rgb_f[n,3] | disp_f[n] | acc_f[n] | w_last[n], n = rows*width, 11*n floats.  Synchronises `stream`. */
+int nfb_render_frame_host(NfbHandle* h, const float pose[12], const double intrinsics[4],
+                          int height, int width, int row_begin, int rows, float near_, float far_,
+                          const float* expression_host, const float* latent_host,
+                          const float* background_host /* [rows*width,3] or NULL */,
+                          const NfbSampling* sampling, float* out_host, void* stream);
+
+/* Number of kernel launches issued by this handle so far (all kernels of this library). */
+int nfb_launch_count(NfbHandle* h, long long* out);
+
+/* Host helper: out[i] = torch.linspace(0, 1, n)[i] bit-for-bit (ATen's CPU kernel: step = 1/(n-1) in
+ * FP32; first half start + i*step, second half end - (n-1-i)*step).  Used for t_coarse / u_fine when the
+ * caller passes NULL.  No CUDA involved. */
+int nfb_host_linspace(float* out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFB_H_ */
