@@ -160,12 +160,53 @@ class Renderer:
         out["_keep"] = keep  # inputs must outlive the asynchronous launch
         return out
 
+    def render_camera(self, pose, intrinsics, height, width, row_begin, rows, near, far, num_coarse, num_fine,
+                      background=None, out=None, precision=None, white_bkgd=False):
+        """Deterministic render of image rows [row_begin, row_begin+rows) with in-kernel ray generation
+        (no o/d tensors in HBM).  pose: 3x4 / 4x4 CPU tensor; background: [rows*width,3] CUDA tensor or None.
+        `out`: optional preallocated [11, rows*width] CUDA buffer; returns the dict of output views."""
+        dev = self.device
+        n = rows * width
+        if out is None:
+            out = torch.empty((11, n), device=dev, dtype=torch.float32)
+        flat = out.view(-1)
+        views = dict(rgb_coarse=flat[0:3 * n].view(n, 3), disp_coarse=flat[3 * n:4 * n], acc_coarse=flat[4 * n:5 * n],
+                     rgb_fine=flat[5 * n:8 * n].view(n, 3), disp_fine=flat[8 * n:9 * n], acc_fine=flat[9 * n:10 * n],
+                     w_last=flat[10 * n:11 * n])
+        rays = capi.NfbRays()
+        rays.n_rays = n
+        p = pose.detach().cpu().float().reshape(-1)
+        rows34 = p[:12] if p.numel() in (12, 16) else None
+        for i in range(12):
+            rays.pose[i] = float(rows34[i])
+        for i in range(4):
+            rays.intrinsics[i] = float(intrinsics[i])
+        rays.height, rays.width, rays.row_begin = height, width, row_begin
+        rays.near_, rays.far_ = float(near), float(far)
+        if background is not None:
+            rays.background = background.data_ptr()
+        prec = precision or _precision
+        has_fine = num_fine > 0
+        sm = capi.NfbSampling(num_coarse, num_fine, 0, 0.0, int(bool(white_bkgd)), 0,
+                              capi.NFB_PREC_EXACT if prec == "exact" else capi.NFB_PREC_FAST,
+                              self.linspace(num_coarse).data_ptr(), self.linspace(num_fine).data_ptr() if has_fine else None)
+        o = capi.NfbOutputs(views["rgb_coarse"].data_ptr(), views["disp_coarse"].data_ptr(), views["acc_coarse"].data_ptr(),
+                            views["rgb_fine"].data_ptr() if has_fine else None,
+                            views["disp_fine"].data_ptr() if has_fine else None,
+                            views["acc_fine"].data_ptr() if has_fine else None, views["w_last"].data_ptr())
+        capi.check(capi.lib.nfb_render_forward(self._h, C.byref(rays), C.byref(sm), None, C.byref(o), None, _stream()),
+                   "render_forward")
+        views["_buf"] = out
+        return views
+
     def render_frame_host(self, pose, intrinsics, height, width, row_begin, rows, near, far, expr_host, latent_host,
                           bg_host, num_coarse, num_fine, out_host, precision=None, white_bkgd=False):
         """Host-buffer end-to-end call (bench e2e leg).  All tensors are CPU (ideally pinned) FP32."""
         prec = precision or _precision
         sm = capi.NfbSampling(num_coarse, num_fine, 0, 0.0, int(bool(white_bkgd)), 0,
-                              capi.NFB_PREC_EXACT if prec == "exact" else capi.NFB_PREC_FAST, None, None)
+                              capi.NFB_PREC_EXACT if prec == "exact" else capi.NFB_PREC_FAST,
+                              self.linspace(num_coarse).data_ptr(),
+                              self.linspace(num_fine).data_ptr() if num_fine > 0 else None)
         pose_a = (C.c_float * 12)(*[float(v) for v in pose.reshape(-1)[:12]])
         intr_a = (C.c_double * 4)(*[float(v) for v in intrinsics])
         capi.check(capi.lib.nfb_render_frame_host(self._h, pose_a, intr_a, height, width, row_begin, rows, float(near),
@@ -177,6 +218,8 @@ _renderers = {}
 
 
 def renderer_for(device: torch.device) -> Renderer:
+    if device.type != "cuda":
+        raise RuntimeError("the nfb render path runs on CUDA (sm_100a) only; there is no CPU fallback")
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     r = _renderers.get(key)
     if r is None:
