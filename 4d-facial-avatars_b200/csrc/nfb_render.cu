@@ -148,6 +148,22 @@ __device__ __forceinline__ void epi_chunk(uint32_t t_acc, uint32_t t_ahi, uint32
   if constexpr (EXACT) tmem_st16(t_alo, lo);
 }
 
+// Optional phase timers (NfbDebug.prof): cycles of one observer thread per role, summed over CTAs.
+struct PhaseTimer {
+  unsigned long long* dst;
+  long long t0;
+  __device__ __forceinline__ PhaseTimer(unsigned long long* d, bool on) : dst(on ? d : nullptr), t0(0) {
+    if (dst) t0 = clock64();
+  }
+  __device__ __forceinline__ void lap(int slot) {
+    if (dst) {
+      const long long t1 = clock64();
+      atomicAdd(dst + slot, (unsigned long long)(t1 - t0));
+      t0 = t1;
+    }
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -267,8 +283,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 
   if (warp == 0) {
     // ============================== weight producer ==============================
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loop; one elected lane issues the copies.
+    {
       uint32_t slot = 0, phase = 0;
+      PhaseTimer tm(p.prof, p.prof != nullptr && lane == 0);
       for (int it = 0; it < n_iter; ++it) {
         for (int t = 0; t < tiles_per_unit; ++t) {
           const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
@@ -283,9 +301,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 #pragma unroll
                 for (int part = 0; part < NPART; ++part) {
                   const uint8_t* src = EXACT ? base + 2 * (size_t)off + part * bytes : base + off;
+                  tm.lap(40);
                   mbar_wait(bar_empty + slot * 8, phase ^ 1);
-                  mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
-                  bulk_g2s(smem_base + kOffRing + slot * kMaxUnitBytes, src, bytes, bar_full + slot * 8);
+                  tm.lap(41);
+                  if (elect_one()) {
+                    mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
+                    bulk_g2s(smem_base + kOffRing + slot * kMaxUnitBytes, src, bytes, bar_full + slot * 8);
+                  }
+                  __syncwarp();
                   if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
                 }
               }
@@ -296,15 +319,19 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // Warp-uniform loop (all 32 lanes wait on the barriers); one elected lane issues tcgen05.mma / commit.
+    {
       uint32_t slot = 0, phase = 0, ph_a = 0;
+      PhaseTimer tm(p.prof, p.prof != nullptr && lane == 0);
       const uint64_t pe_desc_hi = umma_smem_desc_sw128(smem_base + kOffPeHi);
       const uint64_t pe_desc_lo = umma_smem_desc_sw128(smem_base + kOffPeLo);
       for (int it = 0; it < n_iter; ++it) {
         for (int t = 0; t < tiles_per_unit; ++t) {
           for (int s = 0; s < kNumSteps; ++s) {
             const StepInfo si = step_info(s);
+            tm.lap(44);
             mbar_wait(bar_aready, ph_a);
+            tm.lap(45);
             ph_a ^= 1;
             tc_fence_after_sync();
             for (int h = 0; h < 2; ++h) {
@@ -318,28 +345,34 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                 const uint32_t a_col = (a - si.pe_first) * 32;  // TMEM columns of this K atom (2 fp16 / column)
 #pragma unroll
                 for (int part = 0; part < NPART; ++part) {
+                  tm.lap(44);
                   mbar_wait(bar_full + slot * 8, phase);
+                  tm.lap(46);
                   tc_fence_after_sync();
                   const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + slot * kMaxUnitBytes);
+                  const bool last_unit = (a == si.k_atoms - 1) && (part == NPART - 1) && (h == 1 || si.nh1 == 0);
+                  if (elect_one()) {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t bd = b_desc + (uint64_t)(ks * 2);  // +32 bytes per 16-element K step
-                    if (from_pe) {
-                      umma_ss(d_tmem, pe_desc_hi + (uint64_t)(ks * 2), bd, idesc, accum);
-                      accum = 1;
-                      if (EXACT && part == 0) umma_ss(d_tmem, pe_desc_lo + (uint64_t)(ks * 2), bd, idesc, 1);
-                    } else {
-                      umma_ts(d_tmem, tmem_base + kColAhi + a_col + ks * 8, bd, idesc, accum);
-                      accum = 1;
-                      if (EXACT && part == 0) umma_ts(d_tmem, tmem_base + kColAlo + a_col + ks * 8, bd, idesc, 1);
+                    for (int ks = 0; ks < 4; ++ks) {
+                      const uint64_t bd = b_desc + (uint64_t)(ks * 2);  // +32 bytes per 16-element K step
+                      const uint32_t acc_flag = (accum | ks) ? 1u : 0u;
+                      if (from_pe) {
+                        umma_ss(d_tmem, pe_desc_hi + (uint64_t)(ks * 2), bd, idesc, acc_flag);
+                        if (EXACT && part == 0) umma_ss(d_tmem, pe_desc_lo + (uint64_t)(ks * 2), bd, idesc, 1);
+                      } else {
+                        umma_ts(d_tmem, tmem_base + kColAhi + a_col + ks * 8, bd, idesc, acc_flag);
+                        if (EXACT && part == 0) umma_ts(d_tmem, tmem_base + kColAlo + a_col + ks * 8, bd, idesc, 1);
+                      }
                     }
+                    umma_commit(bar_empty + slot * 8);           // slot reusable once these MMAs have read it
+                    if (last_unit) umma_commit(bar_accfull);     // whole step done -> row warps may read TMEM
                   }
-                  umma_commit(bar_empty + slot * 8);  // slot reusable once these MMAs have read it
+                  __syncwarp();
+                  accum = 1;
                   if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
                 }
               }
             }
-            umma_commit(bar_accfull);
           }
         }
       }
@@ -363,9 +396,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     const int R = p.rays_per_unit;
     const bool has_bg = p.bg != nullptr;
     uint32_t ph_acc = 0;
+    PhaseTimer tm(p.prof, p.prof != nullptr && row == 0);
 
     for (int it = 0; it < n_iter; ++it) {
       const int unit = blockIdx.x + it * gridDim.x;
+      tm.lap(39);
       // ---- per-ray constants
       if (row < R) {
         RayP& rp = rayp[row];
@@ -409,6 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         }
       }
       named_bar_sync(kRowBarrier, kRowThreads);
+      tm.lap(0);
 
       for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1 && p.nf == 0) break;
@@ -430,6 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           dirbias[row] = acc0;
           dirbias[128 + row] = acc1;
         }
+        tm.lap(1);
 
         for (int t = 0; t < n_tiles; ++t) {
           const int prow = t * 128 + row;  // pass-local row
@@ -487,12 +524,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           fence_proxy_async_smem();  // make the generic-proxy PE stores visible to the tensor core
           if (t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias / carry_z of other threads
           mbar_arrive(bar_aready);
+          tm.lap(2);
 
           float sigma_raw = 0.f;
           for (int s = 0; s < kNumSteps; ++s) {
             mbar_wait(bar_accfull, ph_acc);
             ph_acc ^= 1;
             tc_fence_after_sync();
+            tm.lap(10 + s);
             float* dump = (p.dbg_act && p.dbg_act_step == s && unit == 0 && pass == 0 && t == 0) ? p.dbg_act + row * 256 : nullptr;
             const StepInfo si = step_info(s);
             if (s <= 5) {
@@ -525,9 +564,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               tc_fence_before_sync();
               mbar_arrive(bar_aready);
             }
+            tm.lap(20 + s);
           }
         }  // tiles
         named_bar_sync(kRowBarrier, kRowThreads);
+        tm.lap(3);
 
         // ---- debug dumps of the per-sample tensors
         {
@@ -561,8 +602,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         }
         if (pass == 1 || p.nf == 0) {
           named_bar_sync(kRowBarrier, kRowThreads);  // carry buffers are reused by the next unit
+          tm.lap(4);
           continue;
         }
+        tm.lap(4);
 
         // ---- inverse-CDF resampling (nerf_helpers.py:344-387) on weights[1:-1] over the mid-point bins
         __syncwarp();
@@ -598,6 +641,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             }
         }
         named_bar_sync(kRowBarrier, kRowThreads);
+        tm.lap(5);
         int P = 1;
         while (P < p.s_fine) P <<= 1;
         for (int k = row; k < R * P; k += kRowThreads) {
@@ -625,6 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           scr_sort[k] = val;
         }
         named_bar_sync(kRowBarrier, kRowThreads);
+        tm.lap(6);
         // ---- torch.sort(cat(z, z_samples)) per ray: bitonic network over P (padded with +inf)
         for (int kk = 2; kk <= P; kk <<= 1) {
           for (int j = kk >> 1; j > 0; j >>= 1) {
@@ -645,6 +690,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           carry_z[k] = scr_sort[rr * P + i];
         }
         named_bar_sync(kRowBarrier, kRowThreads);
+        tm.lap(7);
       }  // pass
     }    // units
     tc_fence_before_sync();

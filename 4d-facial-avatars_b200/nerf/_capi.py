@@ -43,7 +43,7 @@ class NfbOutputs(C.Structure):
 
 class NfbDebug(C.Structure):
     _fields_ = [("z_coarse", C.c_void_p), ("raw_coarse", C.c_void_p), ("z_fine", C.c_void_p), ("raw_fine", C.c_void_p),
-                ("act_dump", C.c_void_p), ("act_step", C.c_int32)]
+                ("act_dump", C.c_void_p), ("act_step", C.c_int32), ("prof", C.c_void_p)]
 
 
 class NfbOutGrads(C.Structure):

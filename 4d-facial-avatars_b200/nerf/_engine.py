@@ -161,7 +161,7 @@ class Renderer:
         return out
 
     def render_camera(self, pose, intrinsics, height, width, row_begin, rows, near, far, num_coarse, num_fine,
-                      background=None, out=None, precision=None, white_bkgd=False):
+                      background=None, out=None, precision=None, white_bkgd=False, prof=None):
         """Deterministic render of image rows [row_begin, row_begin+rows) with in-kernel ray generation
         (no o/d tensors in HBM).  pose: 3x4 / 4x4 CPU tensor; background: [rows*width,3] CUDA tensor or None.
         `out`: optional preallocated [11, rows*width] CUDA buffer; returns the dict of output views."""
@@ -194,8 +194,12 @@ class Renderer:
                             views["rgb_fine"].data_ptr() if has_fine else None,
                             views["disp_fine"].data_ptr() if has_fine else None,
                             views["acc_fine"].data_ptr() if has_fine else None, views["w_last"].data_ptr())
-        capi.check(capi.lib.nfb_render_forward(self._h, C.byref(rays), C.byref(sm), None, C.byref(o), None, _stream()),
-                   "render_forward")
+        dbg = None
+        if prof is not None:  # int64[64] CUDA tensor of phase-cycle counters
+            dbg = capi.NfbDebug()
+            dbg.prof = prof.data_ptr()
+        capi.check(capi.lib.nfb_render_forward(self._h, C.byref(rays), C.byref(sm), None, C.byref(o),
+                                               C.byref(dbg) if dbg is not None else None, _stream()), "render_forward")
         views["_buf"] = out
         return views
 

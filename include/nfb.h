@@ -120,6 +120,12 @@ typedef struct {
    * (rays 0.., samples in order).  [128, 256] floats; columns beyond the step's width are untouched. */
   float* act_dump;
   int32_t act_step;
+  /* Phase timers: 64 uint64 cycle counters (zeroed by the caller), accumulated over all CTAs by one observer
+   * thread per warp role.  Slots: 0 ray setup, 1 per-ray direction term, 2 sampling+encoding (prologue),
+   * 10+s wait for tensor-core step s, 20+s epilogue of step s, 3 end-of-pass barrier, 4 compositing,
+   * 5 cdf, 6 inverse-cdf sampling, 7 sort; 41 producer waiting for a free ring slot; 45 MMA issuer waiting for
+   * the A operand, 46 waiting for weights, 44 issuing. */
+  unsigned long long* prof;
 } NfbDebug;
 
 int nfb_version(void);
