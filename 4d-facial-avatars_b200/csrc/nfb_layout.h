@@ -15,7 +15,7 @@
 //   1,2   layers_xyz.1,2             256  256                              TMEM
 //   3     layers_xyz.3               256  320  = PE(63)+pad | h(256)       SMEM atom + TMEM
 //   4,5   layers_xyz.4,5             256  256                              TMEM
-//   6     layers_dir.0∘fc_feat | σ   128+16  256                           TMEM
+//   6     layers_dir.0∘fc_feat | σ   144 (128 + σ at column 128)  256      TMEM
 //   7,8   layers_dir.1,2             128  128                              TMEM
 //   9     fc_rgb                     16 (3 used)  128                      TMEM
 #pragma once
@@ -32,11 +32,11 @@ namespace nfb {
 constexpr int kTileM = 128;      // rows (samples) per tensor-core tile == TMEM lanes
 constexpr int kAtomK = 64;       // fp16 elements per 128-byte swizzle row
 constexpr int kNumSteps = 10;
-constexpr int kMaxUnitBytes = 128 * 128;  // one weight unit: <=128 output rows x 64 K x 2 B
+constexpr int kMaxUnitBytes = 256 * 128;  // one weight unit: <=256 output rows x 64 K x 2 B
 constexpr int kDimXyz = 63, kDimDir = 24, kDimExpr = 76, kDimLatent = 32, kDimCond = 108;
 
 struct StepInfo {
-  int16_t nh0, nh1;   // output columns of half 0 / half 1 (accumulator columns [0,nh0) and [128,128+nh1))
+  int16_t n;          // output columns of the step == N of its tcgen05.mma (accumulator columns [0,n))
   int16_t k_atoms;    // K / 64 including the PE atom
   int16_t pe_first;   // 1: the first K atom is the positional encoding (A from shared memory)
   int16_t bias_off;   // float offset of this step's bias vector in the per-network bias block
@@ -44,22 +44,22 @@ struct StepInfo {
 };
 
 NFB_HD constexpr StepInfo step_info(int s) {
-  return s == 0   ? StepInfo{128, 128, 1, 1, 0, 256}
-         : s == 1 ? StepInfo{128, 128, 4, 0, 256, 256}
-         : s == 2 ? StepInfo{128, 128, 4, 0, 512, 256}
-         : s == 3 ? StepInfo{128, 128, 5, 1, 768, 256}
-         : s == 4 ? StepInfo{128, 128, 4, 0, 1024, 256}
-         : s == 5 ? StepInfo{128, 128, 4, 0, 1280, 256}
-         : s == 6 ? StepInfo{128, 16, 4, 0, 1536, 144}
-         : s == 7 ? StepInfo{128, 0, 2, 0, 1680, 128}
-         : s == 8 ? StepInfo{128, 0, 2, 0, 1808, 128}
-                  : StepInfo{16, 0, 2, 0, 1936, 16};
+  return s == 0   ? StepInfo{256, 1, 1, 0, 256}
+         : s == 1 ? StepInfo{256, 4, 0, 256, 256}
+         : s == 2 ? StepInfo{256, 4, 0, 512, 256}
+         : s == 3 ? StepInfo{256, 5, 1, 768, 256}
+         : s == 4 ? StepInfo{256, 4, 0, 1024, 256}
+         : s == 5 ? StepInfo{256, 4, 0, 1280, 256}
+         : s == 6 ? StepInfo{144, 4, 0, 1536, 144}
+         : s == 7 ? StepInfo{128, 2, 0, 1680, 128}
+         : s == 8 ? StepInfo{128, 2, 0, 1808, 128}
+                  : StepInfo{16, 2, 0, 1936, 16};
 }
 constexpr int kBiasFloats = 1952;  // 6*256 + 144 + 128 + 128 + 16
 
 // Bytes of the FP16 "hi" weights of one step (x1 stream); the x3 stream stores hi then lo per unit.
 NFB_HD constexpr int step_bytes_x1(int s) {
-  return (step_info(s).nh0 + step_info(s).nh1) * step_info(s).k_atoms * 128;
+  return step_info(s).n * step_info(s).k_atoms * 128;
 }
 NFB_HD constexpr int step_offset_x1(int s) {
   int off = 0;
@@ -69,10 +69,8 @@ NFB_HD constexpr int step_offset_x1(int s) {
 constexpr int kStreamBytesX1 = step_offset_x1(kNumSteps);  // 864256
 constexpr int kStreamBytesX3 = 2 * kStreamBytesX1;
 
-// Byte offset of unit (half h, K atom a) inside its step, x1 stream.
-NFB_HD constexpr int unit_offset_in_step(int s, int h, int a) {
-  return h == 0 ? a * step_info(s).nh0 * 128 : step_info(s).k_atoms * step_info(s).nh0 * 128 + a * step_info(s).nh1 * 128;
-}
+// Byte offset of the unit of K atom a inside its step, x1 stream (a unit = all n rows x 64 K).
+NFB_HD constexpr int unit_offset_in_step(int s, int a) { return a * step_info(s).n * 128; }
 // Byte offset of element (row n, k in [0,64)) inside one swizzled unit: 128-byte rows, 16-byte chunks
 // XORed with (row & 7) — the SWIZZLE_128B pattern the UMMA shared-memory descriptor expects.
 NFB_HD constexpr int sw128_offset(int n, int k) { return n * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + ((k & 7) << 1); }

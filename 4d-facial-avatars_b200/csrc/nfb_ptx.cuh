@@ -164,6 +164,12 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
 }
+// Same with ReLU fused into the conversion (negative inputs and NaN become +0).
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
 __device__ __forceinline__ float2 unpack_f16x2(uint32_t p) {
   __half2 h = *reinterpret_cast<__half2*>(&p);
   return __half22float2(h);

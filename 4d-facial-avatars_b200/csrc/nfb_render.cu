@@ -12,11 +12,12 @@
 // the coarse pass (R*Nc sample rows) and the fine pass (R*(Nc+Nf) rows) as 128-row tensor-core tiles.
 // Per tile the MLP is 10 GEMM steps (nfb_layout.h): accumulators live in TMEM, hidden activations are
 // written back to TMEM as FP16 (tcgen05.st) and consumed as the A operand of the next step straight
-// from TMEM, weights stream L2 -> shared memory through the bulk-copy (TMA) engine into an 8-slot ring
-// of pre-swizzled 16 KB units.
+// from TMEM, weights stream L2 -> shared memory through the bulk-copy (TMA) engine into a 4-slot ring
+// of pre-swizzled units (all N rows x 64 K of one layer, <= 32 KB), one tcgen05.mma per 16-wide K step.
 //
-// Warp roles (192 threads): warp 0 lane 0 = weight producer, warp 1 lane 0 = tcgen05.mma issuer (warp 1
-// also owns the TMEM allocation), warps 2..5 = "row" warps: thread <-> TMEM lane <-> sample row.  They
+// Warp roles (320 threads): warp 0 = weight producer, warp 1 = tcgen05.mma issuer (also owns the TMEM
+// allocation), warps 2..9 = "row" warps.  A row warp may only touch the TMEM lane quadrant (warp & 3), so
+// two warps share each quadrant: thread <-> sample row (TMEM lane), and the pair splits the columns.  They
 // do sampling, positional encoding, per-step epilogues (bias, ReLU, FP16 split), compositing,
 // inverse-CDF resampling and the per-ray sort.
 #include <cuda_fp16.h>
@@ -29,14 +30,14 @@
 
 namespace nfb {
 
-constexpr int kNumSlots = 8;
+constexpr int kNumSlots = 4;    // ring of 32 KB weight units
 constexpr int kRowsMax = 1024;  // sample rows of one pass of one unit
-constexpr int kThreads = 192;
-constexpr int kRowThreads = 128;
+constexpr int kThreads = 320;   // producer warp + MMA warp + 8 row warps
+constexpr int kRowThreads = 256;
 constexpr uint32_t kRowBarrier = 1;  // named barrier id of the four row warps
 
 // TMEM column map (512 columns x 128 lanes x 32 bit)
-constexpr uint32_t kColAcc = 0;    // FP32 accumulators: half 0 at +0, half 1 at +128
+constexpr uint32_t kColAcc = 0;    // FP32 accumulators, columns [0, N)
 constexpr uint32_t kColAhi = 256;  // FP16 activations (hi part), 2 K-elements per column, 128 columns
 constexpr uint32_t kColAlo = 384;  // FP16 activations (lo part), exact mode only
 
@@ -95,57 +96,62 @@ __device__ __forceinline__ void pe_sincos(float y, float& s, float& c) {
   }
 }
 
-// Write one row of the 64-lane positional encoding into the swizzled PE buffer(s).
-template <bool EXACT>
-__device__ __forceinline__ void store_pe_row(uint8_t* pe_hi, uint8_t* pe_lo, int row, const float (&f)[64]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a = f[q * 8 + 2 * e], b = f[q * 8 + 2 * e + 1];
-      hi[e] = pack_f16x2(a, b);
-      if constexpr (EXACT) {
-        const float2 hf = unpack_f16x2(hi[e]);
-        lo[e] = pack_f16x2(a - hf.x, b - hf.y);
-      }
-    }
-    const int off = row * 128 + ((q ^ (row & 7)) << 4);
-    *reinterpret_cast<uint4*>(pe_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    if constexpr (EXACT) *reinterpret_cast<uint4*>(pe_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Epilogue of one 32-column accumulator chunk: v = relu(acc + bias (+ extra)); FP16 (hi[,lo]) -> TMEM A.
+// Epilogue math of one 32-column accumulator chunk: x = acc + bias (+ extra); ReLU; FP16 hi (and lo).
 template <bool EXACT>
-__device__ __forceinline__ void epi_chunk(uint32_t t_acc, uint32_t t_ahi, uint32_t t_alo, const float* __restrict__ bias,
-                                          const float* __restrict__ extra, float* __restrict__ dump) {
-  uint32_t v[32];
-  tmem_ld32(t_acc, v);
-  tmem_wait_ld();
-  uint32_t hi[16], lo[16];
+__device__ __forceinline__ void epi_math(const uint32_t (&v)[32], const float* __restrict__ bias, const float* __restrict__ extra,
+                                         float* __restrict__ dump, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+  float x[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias + j);
-    float x0 = __uint_as_float(v[j]) + b.x, x1 = __uint_as_float(v[j + 1]) + b.y;
-    float x2 = __uint_as_float(v[j + 2]) + b.z, x3 = __uint_as_float(v[j + 3]) + b.w;
-    if (extra) {
+    x[j] = __uint_as_float(v[j]) + b.x; x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+    x[j + 2] = __uint_as_float(v[j + 2]) + b.z; x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+  }
+  if (extra) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
       const float4 e = *reinterpret_cast<const float4*>(extra + j);
-      x0 += e.x; x1 += e.y; x2 += e.z; x3 += e.w;
-    }
-    x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
-    if (dump) { dump[j] = x0; dump[j + 1] = x1; dump[j + 2] = x2; dump[j + 3] = x3; }
-    hi[j / 2] = pack_f16x2(x0, x1);
-    hi[j / 2 + 1] = pack_f16x2(x2, x3);
-    if constexpr (EXACT) {
-      const float2 h0 = unpack_f16x2(hi[j / 2]), h1 = unpack_f16x2(hi[j / 2 + 1]);
-      lo[j / 2] = pack_f16x2(x0 - h0.x, x1 - h0.y);
-      lo[j / 2 + 1] = pack_f16x2(x2 - h1.x, x3 - h1.y);
+      x[j] += e.x; x[j + 1] += e.y; x[j + 2] += e.z; x[j + 3] += e.w;
     }
   }
-  tmem_st16(t_ahi, hi);
-  if constexpr (EXACT) tmem_st16(t_alo, lo);
+  if (dump) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dump[j] = fmaxf(x[j], 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    if constexpr (EXACT) {
+      const float a = fmaxf(x[j], 0.f), b = fmaxf(x[j + 1], 0.f);
+      hi[j / 2] = pack_f16x2(a, b);
+      const float2 h = unpack_f16x2(hi[j / 2]);
+      lo[j / 2] = pack_f16x2(a - h.x, b - h.y);
+    } else {
+      hi[j / 2] = pack_relu_f16x2(x[j], x[j + 1]);  // ReLU fused into the conversion
+    }
+  }
+}
+
+// Epilogue of NCH consecutive 32-column chunks, software-pipelined: the TMEM load of chunk c+1 is in flight
+// while chunk c is converted and stored back to TMEM as the next step's A operand.
+template <bool EXACT, int NCH>
+__device__ __forceinline__ void epi_cols(uint32_t t_acc, uint32_t t_ahi, uint32_t t_alo, const float* __restrict__ bias,
+                                         const float* __restrict__ extra, float* __restrict__ dump) {
+  uint32_t va[32], vb[32], hi[16], lo[16];
+  tmem_ld32(t_acc, va);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    tmem_wait_ld();
+    if (c & 1) {
+      if (c + 1 < NCH) tmem_ld32(t_acc + (c + 1) * 32, va);
+      epi_math<EXACT>(vb, bias + c * 32, extra ? extra + c * 32 : nullptr, dump ? dump + c * 32 : nullptr, hi, lo);
+    } else {
+      if (c + 1 < NCH) tmem_ld32(t_acc + (c + 1) * 32, vb);
+      epi_math<EXACT>(va, bias + c * 32, extra ? extra + c * 32 : nullptr, dump ? dump + c * 32 : nullptr, hi, lo);
+    }
+    tmem_st16(t_ahi + c * 16, hi);
+    if constexpr (EXACT) tmem_st16(t_alo + c * 16, lo);
+  }
 }
 
 // Optional phase timers (NfbDebug.prof): cycles of one observer thread per role, summed over CTAs.
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
       mbar_init(bar_full + i * 8, 1);
       mbar_init(bar_empty + i * 8, 1);
     }
-    mbar_init(bar_aready, kRowThreads);
+    mbar_init(bar_aready, kRowThreads);  // every row thread arrives once per step
     mbar_init(bar_accfull, 1);
     mbar_fence_init();
   }
@@ -292,25 +298,21 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
           for (int s = 0; s < kNumSteps; ++s) {
             const StepInfo si = step_info(s);
-            for (int h = 0; h < 2; ++h) {
-              const int nh = h ? si.nh1 : si.nh0;
-              if (nh == 0) continue;
-              const uint32_t bytes = nh * 128;
-              for (int a = 0; a < si.k_atoms; ++a) {
-                const uint32_t off = kStepOff[s] + unit_offset_in_step(s, h, a);
+            const uint32_t bytes = si.n * 128;
+            for (int a = 0; a < si.k_atoms; ++a) {
+              const uint32_t off = kStepOff[s] + unit_offset_in_step(s, a);
 #pragma unroll
-                for (int part = 0; part < NPART; ++part) {
-                  const uint8_t* src = EXACT ? base + 2 * (size_t)off + part * bytes : base + off;
-                  tm.lap(40);
-                  mbar_wait(bar_empty + slot * 8, phase ^ 1);
-                  tm.lap(41);
-                  if (elect_one()) {
-                    mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
-                    bulk_g2s(smem_base + kOffRing + slot * kMaxUnitBytes, src, bytes, bar_full + slot * 8);
-                  }
-                  __syncwarp();
-                  if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+              for (int part = 0; part < NPART; ++part) {
+                const uint8_t* src = EXACT ? base + 2 * (size_t)off + part * bytes : base + off;
+                tm.lap(40);
+                mbar_wait(bar_empty + slot * 8, phase ^ 1);
+                tm.lap(41);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
+                  bulk_g2s(smem_base + kOffRing + slot * kMaxUnitBytes, src, bytes, bar_full + slot * 8);
                 }
+                __syncwarp();
+                if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
               }
             }
           }
@@ -334,43 +336,39 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             tm.lap(45);
             ph_a ^= 1;
             tc_fence_after_sync();
-            for (int h = 0; h < 2; ++h) {
-              const int nh = h ? si.nh1 : si.nh0;
-              if (nh == 0) continue;
-              const uint32_t idesc = umma_idesc_f16(kTileM, nh);
-              const uint32_t d_tmem = tmem_base + kColAcc + h * 128;
-              uint32_t accum = 0;
-              for (int a = 0; a < si.k_atoms; ++a) {
-                const bool from_pe = si.pe_first && a == 0;
-                const uint32_t a_col = (a - si.pe_first) * 32;  // TMEM columns of this K atom (2 fp16 / column)
+            const uint32_t idesc = umma_idesc_f16(kTileM, si.n);
+            const uint32_t d_tmem = tmem_base + kColAcc;
+            uint32_t accum = 0;
+            for (int a = 0; a < si.k_atoms; ++a) {
+              const bool from_pe = si.pe_first && a == 0;
+              const uint32_t a_col = (a - si.pe_first) * 32;  // TMEM columns of this K atom (2 fp16 / column)
 #pragma unroll
-                for (int part = 0; part < NPART; ++part) {
-                  tm.lap(44);
-                  mbar_wait(bar_full + slot * 8, phase);
-                  tm.lap(46);
-                  tc_fence_after_sync();
-                  const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + slot * kMaxUnitBytes);
-                  const bool last_unit = (a == si.k_atoms - 1) && (part == NPART - 1) && (h == 1 || si.nh1 == 0);
-                  if (elect_one()) {
+              for (int part = 0; part < NPART; ++part) {
+                tm.lap(44);
+                mbar_wait(bar_full + slot * 8, phase);
+                tm.lap(46);
+                tc_fence_after_sync();
+                const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + slot * kMaxUnitBytes);
+                const bool last_unit = (a == si.k_atoms - 1) && (part == NPART - 1);
+                if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                      const uint64_t bd = b_desc + (uint64_t)(ks * 2);  // +32 bytes per 16-element K step
-                      const uint32_t acc_flag = (accum | ks) ? 1u : 0u;
-                      if (from_pe) {
-                        umma_ss(d_tmem, pe_desc_hi + (uint64_t)(ks * 2), bd, idesc, acc_flag);
-                        if (EXACT && part == 0) umma_ss(d_tmem, pe_desc_lo + (uint64_t)(ks * 2), bd, idesc, 1);
-                      } else {
-                        umma_ts(d_tmem, tmem_base + kColAhi + a_col + ks * 8, bd, idesc, acc_flag);
-                        if (EXACT && part == 0) umma_ts(d_tmem, tmem_base + kColAlo + a_col + ks * 8, bd, idesc, 1);
-                      }
+                  for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t bd = b_desc + (uint64_t)(ks * 2);  // +32 bytes per 16-element K step
+                    const uint32_t acc_flag = (accum | ks) ? 1u : 0u;
+                    if (from_pe) {
+                      umma_ss(d_tmem, pe_desc_hi + (uint64_t)(ks * 2), bd, idesc, acc_flag);
+                      if (EXACT && part == 0) umma_ss(d_tmem, pe_desc_lo + (uint64_t)(ks * 2), bd, idesc, 1);
+                    } else {
+                      umma_ts(d_tmem, tmem_base + kColAhi + a_col + ks * 8, bd, idesc, acc_flag);
+                      if (EXACT && part == 0) umma_ts(d_tmem, tmem_base + kColAlo + a_col + ks * 8, bd, idesc, 1);
                     }
-                    umma_commit(bar_empty + slot * 8);           // slot reusable once these MMAs have read it
-                    if (last_unit) umma_commit(bar_accfull);     // whole step done -> row warps may read TMEM
                   }
-                  __syncwarp();
-                  accum = 1;
-                  if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+                  umma_commit(bar_empty + slot * 8);        // slot reusable once these MMAs have read it
+                  if (last_unit) umma_commit(bar_accfull);  // whole step done -> row warps may read TMEM
                 }
+                __syncwarp();
+                accum = 1;
+                if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
               }
             }
           }
@@ -381,7 +379,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     // ============================== row warps ==============================
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;     // tile row == TMEM lane
-    const int ew = warp - 2;           // 0..3, ray index for per-ray stages
+    const int ch = (warp - 2) >> 2;    // which half of the columns this warp of the quadrant pair handles
+    const int ew = warp - 2;           // 0..7, ray index for per-ray stages
+    const int etid = ch * 128 + row;   // 0..255
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint8_t* pe_hi = smem + kOffPeHi;
     uint8_t* pe_lo = smem + kOffPeLo;
@@ -396,15 +396,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     const int R = p.rays_per_unit;
     const bool has_bg = p.bg != nullptr;
     uint32_t ph_acc = 0;
-    PhaseTimer tm(p.prof, p.prof != nullptr && row == 0);
+    PhaseTimer tm(p.prof, p.prof != nullptr && etid == 0);
 
     for (int it = 0; it < n_iter; ++it) {
       const int unit = blockIdx.x + it * gridDim.x;
       tm.lap(39);
       // ---- per-ray constants
-      if (row < R) {
-        RayP& rp = rayp[row];
-        const int g = unit * R + row;
+      if (etid < R) {
+        RayP& rp = rayp[etid];
+        const int g = unit * R + etid;
         rp.valid = g < p.n_rays;
         rp.gidx = g;
         if (rp.valid) {
@@ -453,18 +453,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         const int n_tiles = pass ? p.tiles_f : p.tiles_c;
         const float* bias_n = bias_s + pass * kBiasFloats;
 
-        // per-ray additive term of layers_dir.0: W[:, 256:280] . PE_dir  (one output feature per thread)
+        // per-ray additive term of layers_dir.0: W[:, 256:280] . PE_dir  (one output feature x ray per thread)
         {
           const float* wt = p.wd0b_t[pass];
-          float acc0 = 0.f, acc1 = 0.f;
+          const RayP& rq = rayp[ch < R ? ch : 0];
+          float acc0 = 0.f;
 #pragma unroll 4
-          for (int j = 0; j < kDimDir; ++j) {
-            const float w = wt[j * 128 + row];
-            acc0 = fmaf(w, rayp[0].ped[j], acc0);
-            if (R > 1) acc1 = fmaf(w, rayp[1].ped[j], acc1);
-          }
-          dirbias[row] = acc0;
-          dirbias[128 + row] = acc1;
+          for (int j = 0; j < kDimDir; ++j) acc0 = fmaf(wt[j * 128 + row], rq.ped[j], acc0);
+          dirbias[ch * 128 + row] = acc0;
         }
         tm.lap(1);
 
@@ -474,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           const int r = live ? prow / S : 0;
           const int i = live ? prow - r * S : 0;
           const RayP& rp = rayp[r];
-          // ---- sample depth
+          // ---- sample depth (both threads of a row compute it; the first one publishes it)
           float z = 0.f;
           if (live) {
             if (pass == 0) {
@@ -495,30 +491,63 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                 const float tr = rp.valid ? p.t_rand[(size_t)rp.gidx * p.nc + i] : 0.f;
                 z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
               }
-              carry_z[prow] = z;
+              if (ch == 0) carry_z[prow] = z;
             } else {
               z = carry_z[prow];
             }
           }
-          // ---- positional encoding of o + d*z (63 lanes + 1 zero pad), FP16 (hi[,lo]) into the PE buffer
+          // ---- positional encoding of o + d*z: 63 lanes + 1 zero pad, FP16 (hi[,lo]) into the swizzled PE
+          //      buffer.  The two threads of a row write lanes [0,32) and [32,64) respectively.
           {
-            float f[64];
             const float px = __fadd_rn(rp.o[0], __fmul_rn(rp.d[0], z));
             const float py = __fadd_rn(rp.o[1], __fmul_rn(rp.d[1], z));
             const float pz = __fadd_rn(rp.o[2], __fmul_rn(rp.d[2], z));
-            f[0] = px; f[1] = py; f[2] = pz;
+            float f[32];
+            if (ch == 0) {  // lanes 0..31: xyz, frequencies 0..3, sin of frequency 4, cos(x), cos(y) of frequency 4
+              f[0] = px; f[1] = py; f[2] = pz;
 #pragma unroll
-            for (int fr = 0; fr < 10; ++fr) {
-              const float sc = (float)(1 << fr);
-              pe_sincos<EXACT>(px * sc, f[3 + 6 * fr + 0], f[3 + 6 * fr + 3]);
-              pe_sincos<EXACT>(py * sc, f[3 + 6 * fr + 1], f[3 + 6 * fr + 4]);
-              pe_sincos<EXACT>(pz * sc, f[3 + 6 * fr + 2], f[3 + 6 * fr + 5]);
+              for (int fr = 0; fr < 4; ++fr) {
+                const float sc = (float)(1 << fr);
+                pe_sincos<EXACT>(px * sc, f[3 + 6 * fr + 0], f[3 + 6 * fr + 3]);
+                pe_sincos<EXACT>(py * sc, f[3 + 6 * fr + 1], f[3 + 6 * fr + 4]);
+                pe_sincos<EXACT>(pz * sc, f[3 + 6 * fr + 2], f[3 + 6 * fr + 5]);
+              }
+              float cz;
+              pe_sincos<EXACT>(px * 16.f, f[27], f[30]);
+              pe_sincos<EXACT>(py * 16.f, f[28], f[31]);
+              pe_sincos<EXACT>(pz * 16.f, f[29], cz);
+            } else {        // lanes 32..63: cos(z) of frequency 4, frequencies 5..9, zero pad
+              float sz;
+              pe_sincos<EXACT>(pz * 16.f, sz, f[0]);
+#pragma unroll
+              for (int fr = 5; fr < 10; ++fr) {
+                const float sc = (float)(1 << fr);
+                const int b = 6 * fr - 29;  // lane 3 + 6*fr, minus 32
+                pe_sincos<EXACT>(px * sc, f[b + 0], f[b + 3]);
+                pe_sincos<EXACT>(py * sc, f[b + 1], f[b + 4]);
+                pe_sincos<EXACT>(pz * sc, f[b + 2], f[b + 5]);
+              }
+              f[31] = 0.f;
             }
-            f[63] = 0.f;
-            store_pe_row<EXACT>(pe_hi, pe_lo, row, f);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = f[qq * 8 + 2 * e], b = f[qq * 8 + 2 * e + 1];
+                hi[e] = pack_f16x2(a, b);
+                if constexpr (EXACT) {
+                  const float2 hf = unpack_f16x2(hi[e]);
+                  lo[e] = pack_f16x2(a - hf.x, b - hf.y);
+                }
+              }
+              const int off = row * 128 + (((ch * 4 + qq) ^ (row & 7)) << 4);
+              *reinterpret_cast<uint4*>(pe_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              if constexpr (EXACT) *reinterpret_cast<uint4*>(pe_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
             if (p.dbg_act && p.dbg_act_step == -1 && unit == 0 && pass == 0 && t == 0) {
 #pragma unroll
-              for (int k = 0; k < 64; ++k) p.dbg_act[row * 256 + k] = f[k];
+              for (int k = 0; k < 32; ++k) p.dbg_act[row * 256 + ch * 32 + k] = f[k];
             }
           }
           fence_proxy_async_smem();  // make the generic-proxy PE stores visible to the tensor core
@@ -534,24 +563,22 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             tm.lap(10 + s);
             float* dump = (p.dbg_act && p.dbg_act_step == s && unit == 0 && pass == 0 && t == 0) ? p.dbg_act + row * 256 : nullptr;
             const StepInfo si = step_info(s);
-            if (s <= 5) {
-#pragma unroll 1
-              for (int c = 0; c < 8; ++c)
-                epi_chunk<EXACT>(t_lane + kColAcc + c * 32, t_lane + kColAhi + c * 16, t_lane + kColAlo + c * 16,
-                                 bias_n + si.bias_off + c * 32, nullptr, dump ? dump + c * 32 : nullptr);
-            } else if (s <= 8) {
-              const float* extra = (s == 6) ? dirbias + r * 128 : nullptr;
-#pragma unroll 1
-              for (int c = 0; c < 4; ++c)
-                epi_chunk<EXACT>(t_lane + kColAcc + c * 32, t_lane + kColAhi + c * 16, t_lane + kColAlo + c * 16,
-                                 bias_n + si.bias_off + c * 32, extra ? extra + c * 32 : nullptr, dump ? dump + c * 32 : nullptr);
-              if (s == 6) {
+            if (s <= 5) {        // 256 output columns: this thread converts [ch*128, ch*128+128)
+              const int c0 = ch * 128;
+              epi_cols<EXACT, 4>(t_lane + kColAcc + c0, t_lane + kColAhi + c0 / 2, t_lane + kColAlo + c0 / 2,
+                                 bias_n + si.bias_off + c0, nullptr, dump ? dump + c0 : nullptr);
+            } else if (s <= 8) { // 128 output columns: [ch*64, ch*64+64)
+              const int c0 = ch * 64;
+              const float* extra = (s == 6) ? dirbias + r * 128 + c0 : nullptr;
+              epi_cols<EXACT, 2>(t_lane + kColAcc + c0, t_lane + kColAhi + c0 / 2, t_lane + kColAlo + c0 / 2,
+                                 bias_n + si.bias_off + c0, extra, dump ? dump + c0 : nullptr);
+              if (s == 6 && ch == 0) {  // sigma = column 128 of the folded layers_dir.0 | fc_alpha step
                 uint32_t v[4];
                 tmem_ld4(t_lane + kColAcc + 128, v);
                 tmem_wait_ld();
                 sigma_raw = __uint_as_float(v[0]) + bias_n[si.bias_off + 128];
               }
-            } else {
+            } else if (ch == 0) {
               uint32_t v[4];
               tmem_ld4(t_lane + kColAcc, v);
               tmem_wait_ld();
@@ -575,7 +602,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           float* dz = pass ? p.dbg_z_f : p.dbg_z_c;
           float* dr = pass ? p.dbg_raw_f : p.dbg_raw_c;
           if (dz || dr) {
-            for (int k = row; k < rows; k += kRowThreads) {
+            for (int k = etid; k < rows; k += kRowThreads) {
               const int rr = k / S;
               if (!rayp[rr].valid) continue;
               const size_t gi = (size_t)rayp[rr].gidx * S + (k - rr * S);
@@ -644,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         tm.lap(5);
         int P = 1;
         while (P < p.s_fine) P <<= 1;
-        for (int k = row; k < R * P; k += kRowThreads) {
+        for (int k = etid; k < R * P; k += kRowThreads) {
           const int rr = k / P, i = k - rr * P;
           float val = CUDART_INF_F;
           if (i < p.nc) {
@@ -673,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         // ---- torch.sort(cat(z, z_samples)) per ray: bitonic network over P (padded with +inf)
         for (int kk = 2; kk <= P; kk <<= 1) {
           for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int c = row; c < R * (P >> 1); c += kRowThreads) {
+            for (int c = etid; c < R * (P >> 1); c += kRowThreads) {
               const int rr = c / (P >> 1), tq = c - rr * (P >> 1);
               const int i = 2 * tq - (tq & (j - 1));
               const int l = i + j;
@@ -685,7 +712,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             named_bar_sync(kRowBarrier, kRowThreads);
           }
         }
-        for (int k = row; k < R * p.s_fine; k += kRowThreads) {
+        for (int k = etid; k < R * p.s_fine; k += kRowThreads) {
           const int rr = k / p.s_fine, i = k - rr * p.s_fine;
           carry_z[k] = scr_sort[rr * P + i];
         }
