@@ -69,7 +69,8 @@ struct RayP {  // per-ray constants in shared memory (kRayFloats floats)
   float bg[3];
   int gidx;
   float ped[24];
-  float pad[4];
+  float dz;
+  float pad[3];
 };
 static_assert(sizeof(RayP) == kRayFloats * 4, "RayP size");
 
@@ -177,12 +178,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Compositing of one ray by one warp (volume_rendering_utils.py:7-75).  Samples are lane-blocked.
-// raw/z/wbuf index the pass-local row of the ray's first sample.  Returns w of the last sample in
-// every lane.  Writes rgb[3], disp, acc through the given pointers from lane 0 (if non-null).
-__device__ __forceinline__ float composite_ray(const float4* __restrict__ raw, const float* __restrict__ z, float* __restrict__ wbuf,
-                                               int S, const RayP& rp, bool has_bg, float noise_std, const float* __restrict__ noise,
-                                               bool white_bkgd, float* out_rgb, float* out_disp, float* out_acc, int lane) {
+// Compositing of one ray by one warp (volume_rendering_utils.py:7-75).  Samples are lane-blocked.  `pre`
+// holds what the step-9 epilogue prepared per sample: (colour r, g, b, sigma) with colour = sigmoid(rgb raw)
+// — or the raw background colour on the last sample (:29-33) — and sigma = relu(raw + noise) (+1e-6 on the
+// last sample, :52-53).  Returns w of the last sample; lane 0 writes rgb[3], disp, acc.
+__device__ __forceinline__ float composite_ray(const float4* __restrict__ pre, const float* __restrict__ z, float* __restrict__ wbuf,
+                                               int S, float dnorm, bool white_bkgd, float* out_rgb, float* out_disp,
+                                               float* out_acc, int lane) {
   const int per = (S + 31) >> 5;
   const int i0 = lane * per;
   // pass 1: alpha per sample (kept in wbuf), product of (1 - alpha + 1e-10) over this lane's block
@@ -190,14 +192,9 @@ __device__ __forceinline__ float composite_ray(const float4* __restrict__ raw, c
   for (int j = 0; j < per; ++j) {
     const int i = i0 + j;
     if (i < S) {
-      const float zi = z[i];
-      float delta = (i < S - 1) ? __fsub_rn(z[i + 1], zi) : 1e10f;
-      delta = __fmul_rn(delta, rp.dnorm);
-      float sig = raw[i].w;
-      if (noise_std > 0.f) sig = __fadd_rn(sig, __fmul_rn(noise[i], noise_std));
-      sig = fmaxf(sig, 0.f);
-      if (i == S - 1) sig = __fadd_rn(sig, 1e-6f);
-      const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(sig, delta)));
+      float delta = (i < S - 1) ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
+      delta = __fmul_rn(delta, dnorm);
+      const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(pre[i].w, delta)));
       wbuf[i] = alpha;
       prod *= __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
     }
@@ -220,16 +217,8 @@ __device__ __forceinline__ float composite_ray(const float4* __restrict__ raw, c
       const float w = __fmul_rn(alpha, T);
       T *= __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
       wbuf[i] = w;
-      float cr, cg, cb;
-      if (has_bg && i == S - 1) {
-        cr = rp.bg[0]; cg = rp.bg[1]; cb = rp.bg[2];  // background colour is NOT squashed (:29-33)
-      } else {
-        const float4 q = raw[i];
-        cr = 1.f / (1.f + expf(-q.x));
-        cg = 1.f / (1.f + expf(-q.y));
-        cb = 1.f / (1.f + expf(-q.z));
-      }
-      r = fmaf(w, cr, r); g = fmaf(w, cg, g); b = fmaf(w, cb, b);
+      const float4 q = pre[i];
+      r = fmaf(w, q.x, r); g = fmaf(w, q.y, g); b = fmaf(w, q.z, b);
       depth = fmaf(w, z[i], depth);
       acc += w;
       if (i == S - 1) wl = w;
@@ -267,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
       mbar_init(bar_full + i * 8, 1);
       mbar_init(bar_empty + i * 8, 1);
     }
-    mbar_init(bar_aready, kRowThreads);  // every row thread arrives once per step
+    mbar_init(bar_aready, kRowThreads / 32);  // one arrival per row warp per step
     mbar_init(bar_accfull, 1);
     mbar_fence_init();
   }
@@ -425,23 +414,24 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           rp.d[0] = d0; rp.d[1] = d1; rp.d[2] = d2;
           rp.dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
           if (has_bg) { rp.bg[0] = p.bg[3 * g]; rp.bg[1] = p.bg[3 * g + 1]; rp.bg[2] = p.bg[3 * g + 2]; }
-          // direction encoder input is (d_z, near, far): run_network reads ray_batch[..., -3:] (train_utils.py:14)
-          const float v[3] = {p.dir_z ? p.dir_z[g] : d2, p.near_, p.far_};
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float sn, cs;
-              sincosf(v[c] * (float)(1 << f), &sn, &cs);
-              rp.ped[6 * f + c] = sn;
-              rp.ped[6 * f + 3 + c] = cs;
-            }
-          }
+          rp.dz = p.dir_z ? p.dir_z[g] : d2;
         } else {
           for (int k = 0; k < 3; ++k) { rp.o[k] = 0.f; rp.d[k] = 0.f; rp.bg[k] = 0.f; }
           rp.dnorm = 0.f;
-          for (int k = 0; k < 24; ++k) rp.ped[k] = 0.f;
+          rp.dz = 0.f;
         }
+      }
+      named_bar_sync(kRowBarrier, kRowThreads);
+      // direction encoder input is (d_z, near, far): run_network reads ray_batch[..., -3:] (train_utils.py:14);
+      // one accurate sincos per thread
+      if (etid < R * 12) {
+        const int rr = etid / 12, k = etid - rr * 12, f = k / 3, c = k - f * 3;
+        RayP& rp = rayp[rr];
+        const float v = (c == 0) ? rp.dz : (c == 1 ? p.near_ : p.far_);
+        float sn, cs;
+        sincosf(v * (float)(1 << f), &sn, &cs);
+        rp.ped[6 * f + c] = rp.valid ? sn : 0.f;
+        rp.ped[6 * f + 3 + c] = rp.valid ? cs : 0.f;
       }
       named_bar_sync(kRowBarrier, kRowThreads);
       tm.lap(0);
@@ -453,24 +443,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         const int n_tiles = pass ? p.tiles_f : p.tiles_c;
         const float* bias_n = bias_s + pass * kBiasFloats;
 
-        // per-ray additive term of layers_dir.0: W[:, 256:280] . PE_dir  (one output feature x ray per thread)
-        {
-          const float* wt = p.wd0b_t[pass];
-          const RayP& rq = rayp[ch < R ? ch : 0];
-          float acc0 = 0.f;
-#pragma unroll 4
-          for (int j = 0; j < kDimDir; ++j) acc0 = fmaf(wt[j * 128 + row], rq.ped[j], acc0);
-          dirbias[ch * 128 + row] = acc0;
-        }
-        tm.lap(1);
-
-        for (int t = 0; t < n_tiles; ++t) {
-          const int prow = t * 128 + row;  // pass-local row
+        // ---- prologue of tile t: sample depth + positional encoding -> PE buffer.  Called at the start of a pass
+        //      for tile 0, and for tile t+1 from inside tile t (after step 3 released the PE buffer) so that it
+        //      overlaps the tensor-core work of steps 4..9.
+        auto prologue = [&](int t) {
+          const int prow = t * 128 + row;
           const bool live = prow < rows;
           const int r = live ? prow / S : 0;
           const int i = live ? prow - r * S : 0;
           const RayP& rp = rayp[r];
-          // ---- sample depth (both threads of a row compute it; the first one publishes it)
           float z = 0.f;
           if (live) {
             if (pass == 0) {
@@ -496,64 +477,84 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               z = carry_z[prow];
             }
           }
-          // ---- positional encoding of o + d*z: 63 lanes + 1 zero pad, FP16 (hi[,lo]) into the swizzled PE
-          //      buffer.  The two threads of a row write lanes [0,32) and [32,64) respectively.
-          {
-            const float px = __fadd_rn(rp.o[0], __fmul_rn(rp.d[0], z));
-            const float py = __fadd_rn(rp.o[1], __fmul_rn(rp.d[1], z));
-            const float pz = __fadd_rn(rp.o[2], __fmul_rn(rp.d[2], z));
-            float f[32];
-            if (ch == 0) {  // lanes 0..31: xyz, frequencies 0..3, sin of frequency 4, cos(x), cos(y) of frequency 4
-              f[0] = px; f[1] = py; f[2] = pz;
+          // positional encoding of o + d*z: 63 lanes + 1 zero pad, FP16 (hi[,lo]) into the swizzled PE buffer.
+          // The two threads of a row write lanes [0,32) and [32,64) respectively.
+          const float px = __fadd_rn(rp.o[0], __fmul_rn(rp.d[0], z));
+          const float py = __fadd_rn(rp.o[1], __fmul_rn(rp.d[1], z));
+          const float pz = __fadd_rn(rp.o[2], __fmul_rn(rp.d[2], z));
+          float f[32];
+          if (ch == 0) {  // lanes 0..31: xyz, frequencies 0..3, sin of frequency 4, cos(x), cos(y) of frequency 4
+            f[0] = px; f[1] = py; f[2] = pz;
 #pragma unroll
-              for (int fr = 0; fr < 4; ++fr) {
-                const float sc = (float)(1 << fr);
-                pe_sincos<EXACT>(px * sc, f[3 + 6 * fr + 0], f[3 + 6 * fr + 3]);
-                pe_sincos<EXACT>(py * sc, f[3 + 6 * fr + 1], f[3 + 6 * fr + 4]);
-                pe_sincos<EXACT>(pz * sc, f[3 + 6 * fr + 2], f[3 + 6 * fr + 5]);
-              }
-              float cz;
-              pe_sincos<EXACT>(px * 16.f, f[27], f[30]);
-              pe_sincos<EXACT>(py * 16.f, f[28], f[31]);
-              pe_sincos<EXACT>(pz * 16.f, f[29], cz);
-            } else {        // lanes 32..63: cos(z) of frequency 4, frequencies 5..9, zero pad
-              float sz;
-              pe_sincos<EXACT>(pz * 16.f, sz, f[0]);
-#pragma unroll
-              for (int fr = 5; fr < 10; ++fr) {
-                const float sc = (float)(1 << fr);
-                const int b = 6 * fr - 29;  // lane 3 + 6*fr, minus 32
-                pe_sincos<EXACT>(px * sc, f[b + 0], f[b + 3]);
-                pe_sincos<EXACT>(py * sc, f[b + 1], f[b + 4]);
-                pe_sincos<EXACT>(pz * sc, f[b + 2], f[b + 5]);
-              }
-              f[31] = 0.f;
+            for (int fr = 0; fr < 4; ++fr) {
+              const float sc = (float)(1 << fr);
+              pe_sincos<EXACT>(px * sc, f[3 + 6 * fr + 0], f[3 + 6 * fr + 3]);
+              pe_sincos<EXACT>(py * sc, f[3 + 6 * fr + 1], f[3 + 6 * fr + 4]);
+              pe_sincos<EXACT>(pz * sc, f[3 + 6 * fr + 2], f[3 + 6 * fr + 5]);
             }
+            float cz;
+            pe_sincos<EXACT>(px * 16.f, f[27], f[30]);
+            pe_sincos<EXACT>(py * 16.f, f[28], f[31]);
+            pe_sincos<EXACT>(pz * 16.f, f[29], cz);
+          } else {        // lanes 32..63: cos(z) of frequency 4, frequencies 5..9, zero pad
+            float sz;
+            pe_sincos<EXACT>(pz * 16.f, sz, f[0]);
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-              uint32_t hi[4], lo[4];
+            for (int fr = 5; fr < 10; ++fr) {
+              const float sc = (float)(1 << fr);
+              const int b = 6 * fr - 29;  // lane 3 + 6*fr, minus 32
+              pe_sincos<EXACT>(px * sc, f[b + 0], f[b + 3]);
+              pe_sincos<EXACT>(py * sc, f[b + 1], f[b + 4]);
+              pe_sincos<EXACT>(pz * sc, f[b + 2], f[b + 5]);
+            }
+            f[31] = 0.f;
+          }
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float a = f[qq * 8 + 2 * e], b = f[qq * 8 + 2 * e + 1];
-                hi[e] = pack_f16x2(a, b);
-                if constexpr (EXACT) {
-                  const float2 hf = unpack_f16x2(hi[e]);
-                  lo[e] = pack_f16x2(a - hf.x, b - hf.y);
-                }
+          for (int qq = 0; qq < 4; ++qq) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = f[qq * 8 + 2 * e], b = f[qq * 8 + 2 * e + 1];
+              hi[e] = pack_f16x2(a, b);
+              if constexpr (EXACT) {
+                const float2 hf = unpack_f16x2(hi[e]);
+                lo[e] = pack_f16x2(a - hf.x, b - hf.y);
               }
-              const int off = row * 128 + (((ch * 4 + qq) ^ (row & 7)) << 4);
-              *reinterpret_cast<uint4*>(pe_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              if constexpr (EXACT) *reinterpret_cast<uint4*>(pe_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            if (p.dbg_act && p.dbg_act_step == -1 && unit == 0 && pass == 0 && t == 0) {
+            const int off = row * 128 + (((ch * 4 + qq) ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(pe_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if constexpr (EXACT) *reinterpret_cast<uint4*>(pe_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          if (p.dbg_act && p.dbg_act_step == -1 && unit == 0 && pass == 0 && t == 0) {
 #pragma unroll
-              for (int k = 0; k < 32; ++k) p.dbg_act[row * 256 + ch * 32 + k] = f[k];
-            }
+            for (int k = 0; k < 32; ++k) p.dbg_act[row * 256 + ch * 32 + k] = f[k];
           }
           fence_proxy_async_smem();  // make the generic-proxy PE stores visible to the tensor core
-          if (t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias / carry_z of other threads
-          mbar_arrive(bar_aready);
-          tm.lap(2);
+        };
+
+        prologue(0);
+        named_bar_sync(kRowBarrier, kRowThreads);  // carry_z of this pass is complete (coarse: written above)
+        tm.lap(2);
+
+        for (int t = 0; t < n_tiles; ++t) {
+          const int prow = t * 128 + row;  // pass-local row
+          const bool live = prow < rows;
+          const int r = live ? prow / S : 0;
+          const int i = live ? prow - r * S : 0;
+          const RayP& rp = rayp[r];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_aready);   // PE buffer of tile t is in place (fenced inside prologue)
+          if (t == 0) {
+            // per-ray additive term of layers_dir.0: W[:, 256:280] . PE_dir (one output feature x ray per thread),
+            // computed while the tensor core runs step 0; published by the barrier before step 6.
+            const float* wt = p.wd0b_t[pass];
+            const RayP& rq = rayp[ch < R ? ch : 0];
+            float acc0 = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < kDimDir; ++j) acc0 = fmaf(wt[j * 128 + row], rq.ped[j], acc0);
+            dirbias[ch * 128 + row] = acc0;
+            tm.lap(1);
+          }
 
           float sigma_raw = 0.f;
           for (int s = 0; s < kNumSteps; ++s) {
@@ -569,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                                  bias_n + si.bias_off + c0, nullptr, dump ? dump + c0 : nullptr);
             } else if (s <= 8) { // 128 output columns: [ch*64, ch*64+64)
               const int c0 = ch * 64;
+              if (s == 6 && t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias written by all threads
               const float* extra = (s == 6) ? dirbias + r * 128 + c0 : nullptr;
               epi_cols<EXACT, 2>(t_lane + kColAcc + c0, t_lane + kColAhi + c0 / 2, t_lane + kColAlo + c0 / 2,
                                  bias_n + si.bias_off + c0, extra, dump ? dump + c0 : nullptr);
@@ -579,35 +581,60 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                 sigma_raw = __uint_as_float(v[0]) + bias_n[si.bias_off + 128];
               }
             } else if (ch == 0) {
+              // fc_rgb output.  Prepare what compositing needs per sample: colour and sigma
+              // (volume_rendering_utils.py:29-33, 41-53); the exp(-sigma*delta) needs the neighbour depth and
+              // stays in composite_ray.
               uint32_t v[4];
               tmem_ld4(t_lane + kColAcc, v);
               tmem_wait_ld();
               const float* b = bias_n + si.bias_off;
-              if (live) carry_raw[prow] = make_float4(__uint_as_float(v[0]) + b[0], __uint_as_float(v[1]) + b[1],
-                                                       __uint_as_float(v[2]) + b[2], sigma_raw);
+              if (live) {
+                const float r0 = __uint_as_float(v[0]) + b[0], r1 = __uint_as_float(v[1]) + b[1], r2 = __uint_as_float(v[2]) + b[2];
+                if (rp.valid) {
+                  float* dr = pass ? p.dbg_raw_f : p.dbg_raw_c;
+                  if (dr) reinterpret_cast<float4*>(dr)[(size_t)rp.gidx * S + i] = make_float4(r0, r1, r2, sigma_raw);
+                }
+                float sig = sigma_raw;
+                if (p.noise_std > 0.f && rp.valid)
+                  sig = __fadd_rn(sig, __fmul_rn((pass ? p.noise_f : p.noise_c)[(size_t)rp.gidx * S + i], p.noise_std));
+                sig = fmaxf(sig, 0.f);
+                float4 pre;
+                if (i == S - 1) {
+                  sig = __fadd_rn(sig, 1e-6f);
+                  if (has_bg) { pre.x = rp.bg[0]; pre.y = rp.bg[1]; pre.z = rp.bg[2]; }
+                }
+                if (!(has_bg && i == S - 1)) {
+                  pre.x = 1.f / (1.f + expf(-r0));
+                  pre.y = 1.f / (1.f + expf(-r1));
+                  pre.z = 1.f / (1.f + expf(-r2));
+                }
+                pre.w = sig;
+                carry_raw[prow] = pre;
+              }
             }
             if (s < kNumSteps - 1) {
               tmem_wait_st();
               tc_fence_before_sync();
-              mbar_arrive(bar_aready);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_aready);
             }
             tm.lap(20 + s);
+            if (s == 3 && t + 1 < n_tiles) {  // PE buffer is free: encode the next tile under steps 4..9
+              prologue(t + 1);
+              tm.lap(2);
+            }
           }
         }  // tiles
         named_bar_sync(kRowBarrier, kRowThreads);
         tm.lap(3);
 
-        // ---- debug dumps of the per-sample tensors
+        // ---- debug dump of the sample depths
         {
           float* dz = pass ? p.dbg_z_f : p.dbg_z_c;
-          float* dr = pass ? p.dbg_raw_f : p.dbg_raw_c;
-          if (dz || dr) {
+          if (dz) {
             for (int k = etid; k < rows; k += kRowThreads) {
               const int rr = k / S;
-              if (!rayp[rr].valid) continue;
-              const size_t gi = (size_t)rayp[rr].gidx * S + (k - rr * S);
-              if (dz) dz[gi] = carry_z[k];
-              if (dr) reinterpret_cast<float4*>(dr)[gi] = carry_raw[k];
+              if (rayp[rr].valid) dz[(size_t)rayp[rr].gidx * S + (k - rr * S)] = carry_z[k];
             }
           }
         }
@@ -616,14 +643,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         if (ew < R && rayp[ew].valid) {
           const RayP& rp = rayp[ew];
           const int g = rp.gidx;
-          const float* nz = nullptr;
-          if (p.noise_std > 0.f) nz = (pass ? p.noise_f : p.noise_c) + (size_t)g * S;
           float* o_rgb = pass ? p.rgb_f : p.rgb_c;
           float* o_disp = pass ? p.disp_f : p.disp_c;
           float* o_acc = pass ? p.acc_f : p.acc_c;
-          const float wl = composite_ray(carry_raw + ew * S, carry_z + ew * S, scr_w + ew * S, S, rp, has_bg, p.noise_std, nz,
-                                         p.white_bkgd != 0, o_rgb ? o_rgb + 3 * (size_t)g : nullptr,
-                                         o_disp ? o_disp + g : nullptr, o_acc ? o_acc + g : nullptr, lane);
+          const float wl = composite_ray(carry_raw + ew * S, carry_z + ew * S, scr_w + ew * S, S, rp.dnorm, p.white_bkgd != 0,
+                                         o_rgb ? o_rgb + 3 * (size_t)g : nullptr, o_disp ? o_disp + g : nullptr,
+                                         o_acc ? o_acc + g : nullptr, lane);
           const bool last_pass = (pass == 1) || (p.nf == 0);
           if (last_pass && lane == 0 && p.w_last) p.w_last[g] = wl;
         }
@@ -669,14 +694,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         }
         named_bar_sync(kRowBarrier, kRowThreads);
         tm.lap(5);
-        int P = 1;
-        while (P < p.s_fine) P <<= 1;
-        for (int k = etid; k < R * P; k += kRowThreads) {
-          const int rr = k / P, i = k - rr * P;
-          float val = CUDART_INF_F;
+        // cat(z_coarse, z_samples) per ray into scr_sort (stride s_fine)
+        const int SF = p.s_fine;
+        for (int k = etid; k < R * SF; k += kRowThreads) {
+          const int rr = k / SF, i = k - rr * SF;
+          float val;
           if (i < p.nc) {
             val = carry_z[rr * p.nc + i];
-          } else if (i < p.s_fine) {
+          } else {
             const int j = i - p.nc;
             const float* cdf = scr_cdf + rr * p.nc;
             const float* bins = scr_bins + rr * p.nc;
@@ -697,24 +722,33 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         }
         named_bar_sync(kRowBarrier, kRowThreads);
         tm.lap(6);
-        // ---- torch.sort(cat(z, z_samples)) per ray: bitonic network over P (padded with +inf)
-        for (int kk = 2; kk <= P; kk <<= 1) {
-          for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int c = etid; c < R * (P >> 1); c += kRowThreads) {
-              const int rr = c / (P >> 1), tq = c - rr * (P >> 1);
-              const int i = 2 * tq - (tq & (j - 1));
-              const int l = i + j;
-              float* a = scr_sort + rr * P;
-              const float x = a[i], y = a[l];
-              const bool up = (i & kk) == 0;
-              if ((x > y) == up) { a[i] = y; a[l] = x; }
+        // ---- torch.sort(cat(z, z_samples)) (train_utils.py:126) as a rank merge: the coarse depths are sorted, the
+        //      samples need not be (stochastic u), so an element's rank = (# coarse before it, by binary search)
+        //      + (# samples before it, counted).  Ties: coarse first, then samples by index — equal values make any
+        //      tie order give the same sorted array.
+        for (int k = etid; k < R * SF; k += kRowThreads) {
+          const int rr = k / SF, i = k - rr * SF;
+          const float* zc = scr_sort + rr * SF;
+          const float* zs = zc + p.nc;
+          const float v = zc[i];
+          int rank;
+          if (i < p.nc) {
+            rank = i;
+            for (int j = 0; j < p.nf; ++j) rank += (zs[j] < v) ? 1 : 0;
+          } else {
+            const int jm = i - p.nc;
+            int lo = 0, hi = p.nc;  // # coarse depths <= v
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (zc[mid] <= v) lo = mid + 1; else hi = mid;
             }
-            named_bar_sync(kRowBarrier, kRowThreads);
+            rank = lo;
+            for (int j = 0; j < p.nf; ++j) {
+              const float y = zs[j];
+              rank += (y < v || (y == v && j < jm)) ? 1 : 0;
+            }
           }
-        }
-        for (int k = etid; k < R * p.s_fine; k += kRowThreads) {
-          const int rr = k / p.s_fine, i = k - rr * p.s_fine;
-          carry_z[k] = scr_sort[rr * P + i];
+          carry_z[rr * SF + rank] = v;
         }
         named_bar_sync(kRowBarrier, kRowThreads);
         tm.lap(7);
