@@ -266,6 +266,11 @@ def main():
         k_ms = kernel_ms / a.steps
         achieved = flop_per_launch / (k_ms * 1e-3) / 1e12
         peak = pk["bf16_tflops"]
+        traffic = None  # dram bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+        tpath = os.path.join(ROOT, "profiles", "r1_render_kernel_ncu.json")
+        if os.path.exists(tpath) and (H, W, nc, nf, a.precision) == (512, 512, 64, 128, "fast"):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
         # in-run parity: two image rows of the last rendered frame against the oracle
         last = (a.warmup + a.steps - 1) % len(frames)
         v = step_resident(a.warmup + a.steps - 1)
@@ -312,7 +317,8 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "frac_of_sustained": achieved / pk.get("bf16_tflops_sustained", peak), "peak_source": pk_src,
-                         "kernel": "nfb::render_kernel", "kernel_ms": k_ms, "flop_per_launch": flop_per_launch, "traffic": None},
+                         "kernel": "nfb::render_kernel", "kernel_ms": k_ms, "flop_per_launch": flop_per_launch, "traffic": traffic,
+                         "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/r1_render_kernel_ncu.md)"},
             "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
