@@ -273,9 +273,11 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         # in-run parity: two image rows of the last rendered frame against the oracle
         last = (a.warmup + a.steps - 1) % len(frames)
-        v = step_resident(a.warmup + a.steps - 1)
+        fr, dfr = frames[last], dev_frames[last]
+        eng.set_frame(dfr["expr"], dfr["latent"])  # no collective here: only rank 0 runs the parity check
+        v = eng.render_camera(fr["pose"], fr["intrinsics"], H, W, 0, H, NEAR, FAR, nc, nf, background=dfr["bg"], out=out_buf,
+                              precision=a.precision)
         torch.cuda.synchronize()
-        fr = frames[last]
         ro, rd = O.ray_bundle(H, W, fr["intrinsics"], fr["pose"])
         rows = slice(H // 2, H // 2 + 2)
         s = O.Sampling(nc, nf, False, 0.0, False, 65536)
@@ -323,6 +325,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
