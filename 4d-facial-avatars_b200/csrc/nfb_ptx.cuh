@@ -156,6 +156,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Explicit shared-space 128-bit load (a generic `ld` on a shared pointer goes through the long-latency path).
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 // ------------------------------------------------------------------ FP16 helpers
 // Two floats -> packed f16x2 with the FIRST argument in the low half (lower K index), round-to-nearest,
 // saturating to +-65504 so an out-of-range activation cannot become inf inside the tensor core.

@@ -58,7 +58,7 @@ constexpr int kOffRay = kOffDirBias + 2 * 128 * 4;
 constexpr int kOffBars = kOffRay + 2 * kRayFloats * 4;
 constexpr int kNumBars = 2 * kNumSlots + 2;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;  // + slack for the 1024-byte alignment
+constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
@@ -97,22 +97,38 @@ __device__ __forceinline__ void pe_sincos(float y, float& s, float& c) {
   }
 }
 
+// Optional phase timers (NfbDebug.prof): cycles of one observer thread per role, summed over CTAs.
+struct PhaseTimer {
+  unsigned long long* dst;
+  long long t0;
+  __device__ __forceinline__ PhaseTimer(unsigned long long* d, bool on) : dst(on ? d : nullptr), t0(0) {
+    if (dst) t0 = clock64();
+  }
+  __device__ __forceinline__ void lap(int slot) {
+    if (dst) {
+      const long long t1 = clock64();
+      atomicAdd(dst + slot, (unsigned long long)(t1 - t0));
+      t0 = t1;
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Epilogue math of one 32-column accumulator chunk: x = acc + bias (+ extra); ReLU; FP16 hi (and lo).
 template <bool EXACT>
-__device__ __forceinline__ void epi_math(const uint32_t (&v)[32], const float* __restrict__ bias, const float* __restrict__ extra,
+__device__ __forceinline__ void epi_math(const uint32_t (&v)[32], uint32_t bias, uint32_t extra,
                                          float* __restrict__ dump, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
-  float x[32];
+  float x[32];  // bias / extra are shared-memory byte addresses (extra == 0: none)
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + j);
+    const float4 b = lds128(bias + j * 4);
     x[j] = __uint_as_float(v[j]) + b.x; x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
     x[j + 2] = __uint_as_float(v[j + 2]) + b.z; x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
   }
   if (extra) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 e = *reinterpret_cast<const float4*>(extra + j);
+      const float4 e = lds128(extra + j * 4);
       x[j] += e.x; x[j + 1] += e.y; x[j + 2] += e.z; x[j + 3] += e.w;
     }
   }
@@ -133,43 +149,44 @@ __device__ __forceinline__ void epi_math(const uint32_t (&v)[32], const float* _
   }
 }
 
-// Epilogue of NCH consecutive 32-column chunks, software-pipelined: the TMEM load of chunk c+1 is in flight
-// while chunk c is converted and stored back to TMEM as the next step's A operand.
+// Epilogue of NCH consecutive 32-column chunks (NCH even).
+//   fast : chunks are handled two at a time — both TMEM loads in flight, then the two independent
+//          bias/convert chains interleave (one warp's chain is ~4 dependent latencies long; with only two
+//          warps per scheduler the extra ILP is what keeps the issue slots busy).
+//   exact: one chunk at a time with the next chunk's load in flight (the hi/lo split needs the registers).
 template <bool EXACT, int NCH>
-__device__ __forceinline__ void epi_cols(uint32_t t_acc, uint32_t t_ahi, uint32_t t_alo, const float* __restrict__ bias,
-                                         const float* __restrict__ extra, float* __restrict__ dump) {
-  uint32_t va[32], vb[32], hi[16], lo[16];
-  tmem_ld32(t_acc, va);
+__device__ __forceinline__ void epi_cols(uint32_t t_acc, uint32_t t_ahi, uint32_t t_alo, uint32_t bias, uint32_t extra,
+                                         float* __restrict__ dump) {
+  if constexpr (EXACT) {
+    uint32_t va[32], vb[32], hi[16], lo[16];
+    tmem_ld32(t_acc, va);
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    tmem_wait_ld();
-    if (c & 1) {
-      if (c + 1 < NCH) tmem_ld32(t_acc + (c + 1) * 32, va);
-      epi_math<EXACT>(vb, bias + c * 32, extra ? extra + c * 32 : nullptr, dump ? dump + c * 32 : nullptr, hi, lo);
-    } else {
-      if (c + 1 < NCH) tmem_ld32(t_acc + (c + 1) * 32, vb);
-      epi_math<EXACT>(va, bias + c * 32, extra ? extra + c * 32 : nullptr, dump ? dump + c * 32 : nullptr, hi, lo);
+    for (int c = 0; c < NCH; ++c) {
+      tmem_wait_ld();
+      if (c & 1) {
+        if (c + 1 < NCH) tmem_ld32(t_acc + (c + 1) * 32, va);
+        epi_math<EXACT>(vb, bias + c * 128, extra ? extra + c * 128 : 0u, dump ? dump + c * 32 : nullptr, hi, lo);
+      } else {
+        if (c + 1 < NCH) tmem_ld32(t_acc + (c + 1) * 32, vb);
+        epi_math<EXACT>(va, bias + c * 128, extra ? extra + c * 128 : 0u, dump ? dump + c * 32 : nullptr, hi, lo);
+      }
+      tmem_st16(t_ahi + c * 16, hi);
+      tmem_st16(t_alo + c * 16, lo);
     }
-    tmem_st16(t_ahi + c * 16, hi);
-    if constexpr (EXACT) tmem_st16(t_alo + c * 16, lo);
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCH; c += 2) {
+      uint32_t va[32], vb[32], ha[16], hb[16], lo[16];
+      tmem_ld32(t_acc + c * 32, va);
+      tmem_ld32(t_acc + (c + 1) * 32, vb);
+      tmem_wait_ld();
+      epi_math<EXACT>(va, bias + c * 128, extra ? extra + c * 128 : 0u, dump ? dump + c * 32 : nullptr, ha, lo);
+      epi_math<EXACT>(vb, bias + (c + 1) * 128, extra ? extra + (c + 1) * 128 : 0u, dump ? dump + (c + 1) * 32 : nullptr, hb, lo);
+      tmem_st16(t_ahi + c * 16, ha);
+      tmem_st16(t_ahi + (c + 1) * 16, hb);
+    }
   }
 }
-
-// Optional phase timers (NfbDebug.prof): cycles of one observer thread per role, summed over CTAs.
-struct PhaseTimer {
-  unsigned long long* dst;
-  long long t0;
-  __device__ __forceinline__ PhaseTimer(unsigned long long* d, bool on) : dst(on ? d : nullptr), t0(0) {
-    if (dst) t0 = clock64();
-  }
-  __device__ __forceinline__ void lap(int slot) {
-    if (dst) {
-      const long long t1 = clock64();
-      atomicAdd(dst + slot, (unsigned long long)(t1 - t0));
-      t0 = t1;
-    }
-  }
-};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -238,9 +255,11 @@ __device__ __forceinline__ float composite_ray(const float4* __restrict__ pre, c
 // ------------------------------------------------------------------------------------------------
 template <bool EXACT>
 __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Use the dynamic shared array directly (no integer round trip) so the compiler keeps the shared address
+  // space and emits LDS/STS instead of generic loads; the swizzled operands need 1024-byte alignment.
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
+  if ((smem_base & 1023u) != 0u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NPART = EXACT ? 2 : 1;
 
@@ -567,13 +586,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             if (s <= 5) {        // 256 output columns: this thread converts [ch*128, ch*128+128)
               const int c0 = ch * 128;
               epi_cols<EXACT, 4>(t_lane + kColAcc + c0, t_lane + kColAhi + c0 / 2, t_lane + kColAlo + c0 / 2,
-                                 bias_n + si.bias_off + c0, nullptr, dump ? dump + c0 : nullptr);
+                                 smem_u32(bias_n + si.bias_off + c0), 0u, dump ? dump + c0 : nullptr);
             } else if (s <= 8) { // 128 output columns: [ch*64, ch*64+64)
               const int c0 = ch * 64;
               if (s == 6 && t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias written by all threads
-              const float* extra = (s == 6) ? dirbias + r * 128 + c0 : nullptr;
+              const uint32_t extra = (s == 6) ? smem_u32(dirbias + r * 128 + c0) : 0u;
               epi_cols<EXACT, 2>(t_lane + kColAcc + c0, t_lane + kColAhi + c0 / 2, t_lane + kColAlo + c0 / 2,
-                                 bias_n + si.bias_off + c0, extra, dump ? dump + c0 : nullptr);
+                                 smem_u32(bias_n + si.bias_off + c0), extra, dump ? dump + c0 : nullptr);
               if (s == 6 && ch == 0) {  // sigma = column 128 of the folded layers_dir.0 | fc_alpha step
                 uint32_t v[4];
                 tmem_ld4(t_lane + kColAcc + 128, v);
