@@ -36,22 +36,22 @@ __global__ void fold_feat_kernel(const float* __restrict__ Wf, const float* __re
   }
 }
 
-// One thread per 16-byte chunk (8 consecutive K) of one weight unit of step `s`.
+// One thread per 16-byte chunk (8 consecutive K) of one weight row of unit `u` of step `s`.
 __global__ void pack_step_kernel(const float* __restrict__ src, int ld, int n_valid, int s, uint8_t* __restrict__ dst_x1,
                                  uint8_t* __restrict__ dst_x3) {
   const StepInfo si = step_info(s);
-  const int n_total = si.n;
-  const int chunks = n_total * si.k_atoms * 8;
+  const int u = blockIdx.y;
+  const UnitInfo ui = unit_info(s, u);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= chunks) return;
+  if (idx >= ui.rows * 8) return;
   const int c16 = idx & 7;
-  const int n = (idx >> 3) % n_total;
-  const int a = (idx >> 3) / n_total;
+  const int n_local = idx >> 3;
+  const int n = (ui.h ? si.nh0 : 0) + n_local;  // row of the step's logical weight matrix
   __align__(16) __half hi[8];
   __align__(16) __half lo[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int k = a * 64 + c16 * 8 + e;  // logical K index of this step
+    const int k = ui.ka * 64 + c16 * 8 + e;  // logical K index of this step
     float w = 0.f;
     if (n < n_valid) {
       if (si.pe_first) {
@@ -64,12 +64,12 @@ __global__ void pack_step_kernel(const float* __restrict__ src, int ld, int n_va
     hi[e] = __float2half_rn(w);
     lo[e] = __float2half_rn(w - __half2float(hi[e]));
   }
-  const size_t unit_x1 = (size_t)step_offset_x1(s) + unit_offset_in_step(s, a);
-  const int inner = n * 128 + ((c16 ^ (n & 7)) << 4);
+  const size_t unit_x1 = (size_t)step_offset_x1(s) + unit_offset_in_step(s, u);
+  const int inner = n_local * 128 + ((c16 ^ (n_local & 7)) << 4);
   *reinterpret_cast<uint4*>(dst_x1 + unit_x1 + inner) = *reinterpret_cast<const uint4*>(hi);
   const size_t unit_x3 = 2 * unit_x1;
   *reinterpret_cast<uint4*>(dst_x3 + unit_x3 + inner) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(dst_x3 + unit_x3 + (size_t)n_total * 128 + inner) = *reinterpret_cast<const uint4*>(lo);
+  *reinterpret_cast<uint4*>(dst_x3 + unit_x3 + (size_t)ui.rows * 128 + inner) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // Static bias block, the 108 conditioning columns of layers_xyz.0/.3 and the transposed direction
@@ -137,9 +137,7 @@ cudaError_t launch_load_weights(NetBuffers& nb, const float* const params[26], c
   const int ld[kNumSteps] = {171, 256, 256, 427, 256, 256, 256, 128, 128, 128};
   const int nv[kNumSteps] = {256, 256, 256, 256, 256, 256, 129, 128, 128, 3};
   for (int s = 0; s < kNumSteps; ++s) {
-    const StepInfo si = step_info(s);
-    const int chunks = si.n * si.k_atoms * 8;
-    pack_step_kernel<<<(chunks + 255) / 256, 256, 0, st>>>(src[s], ld[s], nv[s], s, nb.stream_x1, nb.stream_x3);
+    pack_step_kernel<<<dim3(4, num_units(s)), 256, 0, st>>>(src[s], ld[s], nv[s], s, nb.stream_x1, nb.stream_x3);
     ++*launches;
   }
   return cudaGetLastError();

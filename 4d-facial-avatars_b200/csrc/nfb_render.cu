@@ -12,8 +12,11 @@
 // the coarse pass (R*Nc sample rows) and the fine pass (R*(Nc+Nf) rows) as 128-row tensor-core tiles.
 // Per tile the MLP is 10 GEMM steps (nfb_layout.h): accumulators live in TMEM, hidden activations are
 // written back to TMEM as FP16 (tcgen05.st) and consumed as the A operand of the next step straight
-// from TMEM, weights stream L2 -> shared memory through the bulk-copy (TMA) engine into a 4-slot ring
-// of pre-swizzled units (all N rows x 64 K of one layer, <= 32 KB), one tcgen05.mma per 16-wide K step.
+// from TMEM, weights stream L2 -> shared memory through the bulk-copy (TMA) engine into an 8-slot ring
+// of pre-swizzled 16 KB units (one N-half x one 64-wide K atom), one tcgen05.mma (M=128, N<=128) per 16-wide K step.
+// Each step runs as two N-halves with their own accumulator and "done" barrier, and its units are ordered so that
+// the MMAs that only need the first half of the previous step's output are issued first: the epilogue of one half
+// overlaps the tensor-core work of the other half / the next step (nfb_layout.h).
 //
 // Warp roles (320 threads): warp 0 = weight producer, warp 1 = tcgen05.mma issuer (also owns the TMEM
 // allocation), warps 2..9 = "row" warps.  A row warp may only touch the TMEM lane quadrant (warp & 3), so
@@ -30,16 +33,18 @@
 
 namespace nfb {
 
-constexpr int kNumSlots = 4;    // ring of 32 KB weight units
+constexpr int kNumSlots = 8;    // ring of 16 KB weight units
 constexpr int kRowsMax = 1024;  // sample rows of one pass of one unit
 constexpr int kThreads = 320;   // producer warp + MMA warp + 8 row warps
 constexpr int kRowThreads = 256;
 constexpr uint32_t kRowBarrier = 1;  // named barrier id of the four row warps
 
-// TMEM column map (512 columns x 128 lanes x 32 bit)
-constexpr uint32_t kColAcc = 0;    // FP32 accumulators, columns [0, N)
-constexpr uint32_t kColAhi = 256;  // FP16 activations (hi part), 2 K-elements per column, 128 columns
-constexpr uint32_t kColAlo = 384;  // FP16 activations (lo part), exact mode only
+// TMEM column map (512 columns x 128 lanes x 32 bit): two 256-column regions used alternately.  Step s
+// accumulates into region (s & 1): half 0 in its columns [0,128), half 1 in [128,256).  The epilogue converts each
+// 64-column accumulator slice IN PLACE into FP16: hi part in the slice's first 32 columns (= 64 K elements = one K
+// atom of the next step), lo part (exact mode) in the next 32.  Step s+1 therefore reads its A operand from
+// region (s & 1) at column 64 * atom and accumulates into the other region — no separate activation buffer.
+__device__ __forceinline__ uint32_t region_col(int s) { return (s & 1) ? 256u : 0u; }
 
 // shared memory map (bytes from the 1024-aligned base)
 constexpr int kOffRing = 0;
@@ -56,10 +61,26 @@ constexpr int kOffDirBias = kOffSort + kRowsMax * 4;
 constexpr int kRayFloats = 40;  // o[3] d[3] dnorm valid bg[3] pad PEd[24] ... (see RayP)
 constexpr int kOffRay = kOffDirBias + 2 * 128 * 4;
 constexpr int kOffBars = kOffRay + 2 * kRayFloats * 4;
-constexpr int kNumBars = 2 * kNumSlots + 2;
+constexpr int kNumBars = 2 * kNumSlots + 4;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmemPtr + 16;
-static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0, "alignment");
+constexpr int kMaxProg = 80;                     // weight units per tile (74 with the current step table)
+constexpr int kOffProg = kOffTmemPtr + 16;       // uint4 per unit: the MMA warp's and the producer's "program"
+constexpr int kSmemBytes = kOffProg + kMaxProg * 16;
+static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0 && kOffProg % 16 == 0, "alignment");
+
+// Per-unit program entry, built once per CTA (the step/unit tables of nfb_layout.h involve divisions that are far too
+// slow for the single-lane issue loops):  x = instruction descriptor, y = accumulator column | A column << 16 (TMEM columns
+// relative to the allocation base), z = flags, w = byte offset in the x1 weight stream | rows << 24.
+enum : uint32_t {
+  kUnitFromPe = 1u, kUnitWait0 = 2u, kUnitWait1 = 4u, kUnitFirst = 8u, kUnitCommit0 = 16u, kUnitCommit1 = 32u, kUnitPostWait1 = 64u
+};
+constexpr int total_units() {
+  int n = 0;
+  for (int s = 0; s < kNumSteps; ++s) n += num_units(s);
+  return n;
+}
+constexpr int kTileUnits = total_units();
+static_assert(kTileUnits <= kMaxProg, "program area too small");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 struct RayP {  // per-ray constants in shared memory (kRayFloats floats)
@@ -149,42 +170,22 @@ __device__ __forceinline__ void epi_math(const uint32_t (&v)[32], uint32_t bias,
   }
 }
 
-// Epilogue of NCH consecutive 32-column chunks (NCH even).
-//   fast : chunks are handled two at a time — both TMEM loads in flight, then the two independent
-//          bias/convert chains interleave (one warp's chain is ~4 dependent latencies long; with only two
-//          warps per scheduler the extra ILP is what keeps the issue slots busy).
-//   exact: one chunk at a time with the next chunk's load in flight (the hi/lo split needs the registers).
-template <bool EXACT, int NCH>
-__device__ __forceinline__ void epi_cols(uint32_t t_acc, uint32_t t_ahi, uint32_t t_alo, uint32_t bias, uint32_t extra,
-                                         float* __restrict__ dump) {
+// Epilogue of one 64-column accumulator slice (this thread's share of one N-half): both TMEM loads in flight,
+// two independent bias/ReLU/convert chains, then the FP16 result overwrites the slice in place — hi in columns
+// [0,32), lo (exact mode) in [32,64).  All reads complete (wait::ld) before the first store.
+template <bool EXACT>
+__device__ __forceinline__ void epi_half(uint32_t t_slice, uint32_t bias, uint32_t extra, float* __restrict__ dump) {
+  uint32_t va[32], vb[32], ha[16], hb[16], la[16], lb[16];
+  tmem_ld32(t_slice, va);
+  tmem_ld32(t_slice + 32, vb);
+  tmem_wait_ld();
+  epi_math<EXACT>(va, bias, extra, dump, ha, la);
+  epi_math<EXACT>(vb, bias + 128, extra ? extra + 128 : 0u, dump ? dump + 32 : nullptr, hb, lb);
+  tmem_st16(t_slice, ha);
+  tmem_st16(t_slice + 16, hb);
   if constexpr (EXACT) {
-    uint32_t va[32], vb[32], hi[16], lo[16];
-    tmem_ld32(t_acc, va);
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      tmem_wait_ld();
-      if (c & 1) {
-        if (c + 1 < NCH) tmem_ld32(t_acc + (c + 1) * 32, va);
-        epi_math<EXACT>(vb, bias + c * 128, extra ? extra + c * 128 : 0u, dump ? dump + c * 32 : nullptr, hi, lo);
-      } else {
-        if (c + 1 < NCH) tmem_ld32(t_acc + (c + 1) * 32, vb);
-        epi_math<EXACT>(va, bias + c * 128, extra ? extra + c * 128 : 0u, dump ? dump + c * 32 : nullptr, hi, lo);
-      }
-      tmem_st16(t_ahi + c * 16, hi);
-      tmem_st16(t_alo + c * 16, lo);
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < NCH; c += 2) {
-      uint32_t va[32], vb[32], ha[16], hb[16], lo[16];
-      tmem_ld32(t_acc + c * 32, va);
-      tmem_ld32(t_acc + (c + 1) * 32, vb);
-      tmem_wait_ld();
-      epi_math<EXACT>(va, bias + c * 128, extra ? extra + c * 128 : 0u, dump ? dump + c * 32 : nullptr, ha, lo);
-      epi_math<EXACT>(vb, bias + (c + 1) * 128, extra ? extra + (c + 1) * 128 : 0u, dump ? dump + (c + 1) * 32 : nullptr, hb, lo);
-      tmem_st16(t_ahi + c * 16, ha);
-      tmem_st16(t_ahi + (c + 1) * 16, hb);
-    }
+    tmem_st16(t_slice + 32, la);
+    tmem_st16(t_slice + 48, lb);
   }
 }
 
@@ -265,8 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 
   const uint32_t bar_full = smem_base + kOffBars;               // [kNumSlots]
   const uint32_t bar_empty = bar_full + kNumSlots * 8;          // [kNumSlots]
-  const uint32_t bar_aready = bar_empty + kNumSlots * 8;        // A operand of the next step is in place
-  const uint32_t bar_accfull = bar_aready + 8;                  // all MMAs of the current step completed
+  const uint32_t bar_aready = bar_empty + kNumSlots * 8;        // [2] half-h output of the previous step converted
+  const uint32_t bar_accfull = bar_aready + 16;                 // [2] all MMAs of half h of the current step completed
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
 
@@ -275,8 +276,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
       mbar_init(bar_full + i * 8, 1);
       mbar_init(bar_empty + i * 8, 1);
     }
-    mbar_init(bar_aready, kRowThreads / 32);  // one arrival per row warp per step
-    mbar_init(bar_accfull, 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_aready + h * 8, kRowThreads / 32);  // one arrival per row warp per step
+      mbar_init(bar_accfull + h * 8, 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -287,10 +290,41 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     bias_s[i] = p.bias[0][i];
     bias_s[kBiasFloats + i] = (p.nf > 0) ? p.bias[1][i] : 0.f;
   }
+  if (threadIdx.x < kTileUnits) {
+    int s = 0, u = threadIdx.x;
+    while (u >= num_units(s)) { u -= num_units(s); ++s; }
+    const StepInfo si = step_info(s);
+    const UnitInfo ui = unit_info(s, u);
+    bool first_of_half = true, first_g1 = true, first_g2 = true, any_g2 = false;
+    for (int j = 0; j < num_units(s); ++j) {
+      const UnitInfo uj = unit_info(s, j);
+      if (j < u && uj.h == ui.h) first_of_half = false;
+      if (j < u && uj.group == 1) first_g1 = false;
+      if (j < u && uj.group == 2) first_g2 = false;
+      if (uj.group == 2) any_g2 = true;
+    }
+    uint32_t flags = 0;
+    if (ui.from_pe) flags |= kUnitFromPe;
+    if (ui.group == 1 && first_g1) flags |= kUnitWait0;
+    if (ui.group == 2 && first_g2) flags |= kUnitWait1;
+    if (first_of_half) flags |= kUnitFirst;
+    if (ui.last) flags |= (ui.h ? kUnitCommit1 : kUnitCommit0);
+    if (ui.last && si.nh1 == 0) flags |= kUnitCommit1;                      // single-half step releases both barriers
+    if (u == num_units(s) - 1 && !any_g2) flags |= kUnitPostWait1;          // still consume the half-1 "converted" signal
+    const uint32_t d_col = region_col(s) + ui.h * 128;
+    const uint32_t a_col = (region_col(s) ^ 256u) + (uint32_t)(ui.ka - si.pe_first) * 64u;
+    uint4 e;
+    e.x = umma_idesc_f16(kTileM, ui.rows);
+    e.y = d_col | (a_col << 16);
+    e.z = flags;
+    e.w = (uint32_t)(step_offset_x1(s) + unit_offset_in_step(s, u)) | ((uint32_t)ui.rows << 24);
+    reinterpret_cast<uint4*>(smem + kOffProg)[threadIdx.x] = e;
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_s;
+  const uint4* prog = reinterpret_cast<const uint4*>(smem + kOffProg);
 
   const int n_iter = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tiles_per_unit = p.tiles_c + p.tiles_f;
@@ -304,26 +338,22 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
       for (int it = 0; it < n_iter; ++it) {
         for (int t = 0; t < tiles_per_unit; ++t) {
           const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
-          for (int s = 0; s < kNumSteps; ++s) {
-            const StepInfo si = step_info(s);
-            const uint32_t bytes = si.n * 128;
-            for (int a = 0; a < si.k_atoms; ++a) {
-              const uint32_t off = kStepOff[s] + unit_offset_in_step(s, a);
+          for (int i = 0; i < kTileUnits; ++i) {
+            const uint32_t w = prog[i].w;
+            const uint32_t off = w & 0xFFFFFFu, bytes = (w >> 24) * 128u;
 #pragma unroll
-              for (int part = 0; part < NPART; ++part) {
-                const uint8_t* src = EXACT ? base + 2 * (size_t)off + part * bytes : base + off;
-                tm.lap(40);
-                mbar_wait(bar_empty + slot * 8, phase ^ 1);
-                tm.lap(41);
-                if (elect_one()) {
-                  mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
-                  bulk_g2s(smem_base + kOffRing + slot * kMaxUnitBytes, src, bytes, bar_full + slot * 8);
-                }
-                __syncwarp();
-                if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+            for (int part = 0; part < NPART; ++part) {
+              const uint8_t* src = EXACT ? base + 2 * (size_t)off + part * bytes : base + off;
+              mbar_wait(bar_empty + slot * 8, phase ^ 1);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
+                bulk_g2s(smem_base + kOffRing + slot * kMaxUnitBytes, src, bytes, bar_full + slot * 8);
               }
+              __syncwarp();
+              if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
             }
           }
+          tm.lap(41);
         }
       }
     }
@@ -331,55 +361,60 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     // ============================== MMA issuer ==============================
     // Warp-uniform loop (all 32 lanes wait on the barriers); one elected lane issues tcgen05.mma / commit.
     {
-      uint32_t slot = 0, phase = 0, ph_a = 0;
+      uint32_t slot = 0, phase = 0, ph_a0 = 0, ph_a1 = 0;
       PhaseTimer tm(p.prof, p.prof != nullptr && lane == 0);
       const uint64_t pe_desc_hi = umma_smem_desc_sw128(smem_base + kOffPeHi);
       const uint64_t pe_desc_lo = umma_smem_desc_sw128(smem_base + kOffPeLo);
       for (int it = 0; it < n_iter; ++it) {
         for (int t = 0; t < tiles_per_unit; ++t) {
-          for (int s = 0; s < kNumSteps; ++s) {
-            const StepInfo si = step_info(s);
-            tm.lap(44);
-            mbar_wait(bar_aready, ph_a);
-            tm.lap(45);
-            ph_a ^= 1;
-            tc_fence_after_sync();
-            const uint32_t idesc = umma_idesc_f16(kTileM, si.n);
-            const uint32_t d_tmem = tmem_base + kColAcc;
-            uint32_t accum = 0;
-            for (int a = 0; a < si.k_atoms; ++a) {
-              const bool from_pe = si.pe_first && a == 0;
-              const uint32_t a_col = (a - si.pe_first) * 32;  // TMEM columns of this K atom (2 fp16 / column)
+          for (int i = 0; i < kTileUnits; ++i) {
+            const uint4 e = prog[i];
+            if (e.z & kUnitWait0) {  // group-1 units: previous step's half-0 output (or the PE buffer) is in place
+              mbar_wait(bar_aready, ph_a0);
+              ph_a0 ^= 1;
+              tc_fence_after_sync();
+            }
+            if (e.z & kUnitWait1) {  // group-2 units: previous step's half-1 output is converted too
+              mbar_wait(bar_aready + 8, ph_a1);
+              ph_a1 ^= 1;
+              tc_fence_after_sync();
+            }
+            const uint32_t d_tmem = tmem_base + (e.y & 0xFFFFu);
+            const uint32_t a_tmem = tmem_base + (e.y >> 16);  // hi at +0, lo at +32 (2 fp16 per column)
+            const uint32_t first = (e.z & kUnitFirst) ? 0u : 1u;
 #pragma unroll
-              for (int part = 0; part < NPART; ++part) {
-                tm.lap(44);
-                mbar_wait(bar_full + slot * 8, phase);
-                tm.lap(46);
-                tc_fence_after_sync();
-                const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + slot * kMaxUnitBytes);
-                const bool last_unit = (a == si.k_atoms - 1) && (part == NPART - 1);
-                if (elect_one()) {
+            for (int part = 0; part < NPART; ++part) {
+              mbar_wait(bar_full + slot * 8, phase);
+              tc_fence_after_sync();
+              const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + slot * kMaxUnitBytes);
+              if (elect_one()) {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t bd = b_desc + (uint64_t)(ks * 2);  // +32 bytes per 16-element K step
-                    const uint32_t acc_flag = (accum | ks) ? 1u : 0u;
-                    if (from_pe) {
-                      umma_ss(d_tmem, pe_desc_hi + (uint64_t)(ks * 2), bd, idesc, acc_flag);
-                      if (EXACT && part == 0) umma_ss(d_tmem, pe_desc_lo + (uint64_t)(ks * 2), bd, idesc, 1);
-                    } else {
-                      umma_ts(d_tmem, tmem_base + kColAhi + a_col + ks * 8, bd, idesc, acc_flag);
-                      if (EXACT && part == 0) umma_ts(d_tmem, tmem_base + kColAlo + a_col + ks * 8, bd, idesc, 1);
-                    }
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t bd = b_desc + (uint64_t)(ks * 2);  // +32 bytes per 16-element K step
+                  const uint32_t acc_flag = (first | part | ks) ? 1u : 0u;
+                  if (e.z & kUnitFromPe) {
+                    umma_ss(d_tmem, pe_desc_hi + (uint64_t)(ks * 2), bd, e.x, acc_flag);
+                    if (EXACT && part == 0) umma_ss(d_tmem, pe_desc_lo + (uint64_t)(ks * 2), bd, e.x, 1);
+                  } else {
+                    umma_ts(d_tmem, a_tmem + ks * 8, bd, e.x, acc_flag);
+                    if (EXACT && part == 0) umma_ts(d_tmem, a_tmem + 32 + ks * 8, bd, e.x, 1);
                   }
-                  umma_commit(bar_empty + slot * 8);        // slot reusable once these MMAs have read it
-                  if (last_unit) umma_commit(bar_accfull);  // whole step done -> row warps may read TMEM
                 }
-                __syncwarp();
-                accum = 1;
-                if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+                umma_commit(bar_empty + slot * 8);  // slot reusable once these MMAs have read it
+                if (part == NPART - 1) {
+                  if (e.z & kUnitCommit0) umma_commit(bar_accfull);      // half 0 complete -> its epilogue may start
+                  if (e.z & kUnitCommit1) umma_commit(bar_accfull + 8);  // half 1 complete
+                }
               }
+              __syncwarp();
+              if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+            }
+            if (e.z & kUnitPostWait1) {
+              mbar_wait(bar_aready + 8, ph_a1);
+              ph_a1 ^= 1;
             }
           }
+          tm.lap(44);
         }
       }
     }
@@ -403,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     RayP* rayp = reinterpret_cast<RayP*>(smem + kOffRay);
     const int R = p.rays_per_unit;
     const bool has_bg = p.bg != nullptr;
-    uint32_t ph_acc = 0;
+    uint32_t ph_acc0 = 0, ph_acc1 = 0;
     PhaseTimer tm(p.prof, p.prof != nullptr && etid == 0);
 
     for (int it = 0; it < n_iter; ++it) {
@@ -562,7 +597,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           const int i = live ? prow - r * S : 0;
           const RayP& rp = rayp[r];
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_aready);   // PE buffer of tile t is in place (fenced inside prologue)
+          if (lane == 0) {  // PE buffer of tile t is in place (fenced inside prologue): both gates of step 0
+            mbar_arrive(bar_aready);
+            mbar_arrive(bar_aready + 8);
+          }
           if (t == 0) {
             // per-ray additive term of layers_dir.0: W[:, 256:280] . PE_dir (one output feature x ray per thread),
             // computed while the tensor core runs step 0; published by the barrier before step 6.
@@ -577,34 +615,27 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 
           float sigma_raw = 0.f;
           for (int s = 0; s < kNumSteps; ++s) {
-            mbar_wait(bar_accfull, ph_acc);
-            ph_acc ^= 1;
+            const StepInfo si = step_info(s);
+            const uint32_t t_acc = t_lane + region_col(s);
+            float* dump = (p.dbg_act && p.dbg_act_step == s && unit == 0 && pass == 0 && t == 0) ? p.dbg_act + row * 256 : nullptr;
+            // ---------------- half 0
+            mbar_wait(bar_accfull, ph_acc0);
+            ph_acc0 ^= 1;
             tc_fence_after_sync();
             tm.lap(10 + s);
-            float* dump = (p.dbg_act && p.dbg_act_step == s && unit == 0 && pass == 0 && t == 0) ? p.dbg_act + row * 256 : nullptr;
-            const StepInfo si = step_info(s);
-            if (s <= 5) {        // 256 output columns: this thread converts [ch*128, ch*128+128)
-              const int c0 = ch * 128;
-              epi_cols<EXACT, 4>(t_lane + kColAcc + c0, t_lane + kColAhi + c0 / 2, t_lane + kColAlo + c0 / 2,
-                                 smem_u32(bias_n + si.bias_off + c0), 0u, dump ? dump + c0 : nullptr);
-            } else if (s <= 8) { // 128 output columns: [ch*64, ch*64+64)
-              const int c0 = ch * 64;
+            const bool skip_epi = (p.dbg_act_step == -100);  // timing experiment: tensor-core side alone
+            if (skip_epi) {
+            } else if (s <= 8) {  // ReLU layers: this thread converts output columns [64*ch, 64*ch+64) of the half in place
+              const int c0 = 64 * ch;
               if (s == 6 && t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias written by all threads
               const uint32_t extra = (s == 6) ? smem_u32(dirbias + r * 128 + c0) : 0u;
-              epi_cols<EXACT, 2>(t_lane + kColAcc + c0, t_lane + kColAhi + c0 / 2, t_lane + kColAlo + c0 / 2,
-                                 smem_u32(bias_n + si.bias_off + c0), extra, dump ? dump + c0 : nullptr);
-              if (s == 6 && ch == 0) {  // sigma = column 128 of the folded layers_dir.0 | fc_alpha step
-                uint32_t v[4];
-                tmem_ld4(t_lane + kColAcc + 128, v);
-                tmem_wait_ld();
-                sigma_raw = __uint_as_float(v[0]) + bias_n[si.bias_off + 128];
-              }
+              epi_half<EXACT>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), extra, dump ? dump + c0 : nullptr);
             } else if (ch == 0) {
               // fc_rgb output.  Prepare what compositing needs per sample: colour and sigma
               // (volume_rendering_utils.py:29-33, 41-53); the exp(-sigma*delta) needs the neighbour depth and
               // stays in composite_ray.
               uint32_t v[4];
-              tmem_ld4(t_lane + kColAcc, v);
+              tmem_ld4(t_acc, v);
               tmem_wait_ld();
               const float* b = bias_n + si.bias_off;
               if (live) {
@@ -638,6 +669,28 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               if (lane == 0) mbar_arrive(bar_aready);
             }
             tm.lap(20 + s);
+            // ---------------- half 1
+            mbar_wait(bar_accfull + 8, ph_acc1);
+            ph_acc1 ^= 1;
+            tc_fence_after_sync();
+            tm.lap(30 + (s < 8 ? s : 7));
+            if (skip_epi) {
+            } else if (s <= 5) {
+              const int c0 = 128 + 64 * ch;
+              epi_half<EXACT>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), 0u, dump ? dump + c0 : nullptr);
+            } else if (s == 6 && ch == 0) {  // sigma = first column of half 1 of the folded layers_dir.0 | fc_alpha step
+              uint32_t v[4];
+              tmem_ld4(t_acc + 128, v);
+              tmem_wait_ld();
+              sigma_raw = __uint_as_float(v[0]) + bias_n[si.bias_off + 128];
+            }
+            if (s < kNumSteps - 1) {
+              tmem_wait_st();
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_aready + 8);
+            }
+            tm.lap(48 + s);
             if (s == 3 && t + 1 < n_tiles) {  // PE buffer is free: encode the next tile under steps 4..9
               prologue(t + 1);
               tm.lap(2);

@@ -39,17 +39,17 @@ units = H * W / 2
 tiles = units * 4
 names = {0: "ray setup", 1: "dir term", 2: "prologue (z+PE)", 3: "end-of-pass barrier", 4: "composite", 5: "cdf", 6: "inverse-cdf", 7: "sort",
          39: "loop", 41: "producer: wait free slot", 40: "producer: issue", 44: "mma: issue", 45: "mma: wait A operand", 46: "mma: wait weights"}
-for ck in range(4):
-    names[30 + 2 * ck] = f"  step1 chunk {ck}: wait ld"
-    names[31 + 2 * ck] = f"  step1 chunk {ck}: math+st"
-names[38] = "  step1: wait st + fence"
+names[47] = "mma: wait A operand (half 1)"
 for s in range(10):
-    names[10 + s] = f"wait MMA step {s}"
-    names[20 + s] = f"epilogue step {s}"
-row_total = sum(c[i] for i in list(range(0, 8)) + list(range(10, 39)) + [39])
+    names[10 + s] = f"wait MMA step {s} half 0"
+    names[20 + s] = f"epilogue step {s} half 0"
+    names[48 + s] = f"epilogue step {s} half 1"
+for s in range(8):
+    names[30 + s] = f"wait MMA step {s}{'+' if s == 7 else ''} half 1"
+row_total = sum(c[i] for i in list(range(0, 8)) + list(range(10, 40)) + list(range(48, 58)))
 print(f"{prec} {H}x{W}: {ms:.2f} ms, {H*W/ms*1e3:.3e} rays/s; row-warp observer total {row_total/ctas/1e6:.2f} Mcycles per CTA")
 print(f"{'phase':28s} {'cycles/tile':>12s} {'share':>7s}")
 for i in sorted(names):
     if c[i]:
-        share = c[i] / row_total if i < 40 else c[i] / sum(c[40:48])
+        share = c[i] / row_total if (i < 40 or i >= 48) else c[i] / sum(c[40:48])
         print(f"{names[i]:28s} {c[i]/tiles:12.0f} {100*share:6.1f}%")
