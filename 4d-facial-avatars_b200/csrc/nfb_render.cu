@@ -36,6 +36,7 @@ namespace nfb {
 constexpr int kNumSlots = 8;    // ring of 16 KB weight units
 constexpr int kRowsMax = 1024;  // sample rows of one pass of one unit
 constexpr int kThreads = 320;   // producer warp + MMA warp + 8 row warps
+constexpr int kCluster = 2;     // CTAs (SMs) per cluster sharing every weight unit through one multicast L2 read
 constexpr int kRowThreads = 256;
 constexpr uint32_t kRowBarrier = 1;  // named barrier id of the four row warps
 
@@ -81,6 +82,48 @@ constexpr int total_units() {
 }
 constexpr int kTileUnits = total_units();
 static_assert(kTileUnits <= kMaxProg, "program area too small");
+
+struct ProgEntry { uint32_t x, y, z, w; };
+struct ProgTable { ProgEntry e[kMaxProg]; };
+constexpr uint32_t region_col_c(int s) { return (s & 1) ? 256u : 0u; }
+constexpr ProgTable make_prog() {
+  ProgTable t{};
+  int i = 0;
+  for (int s = 0; s < kNumSteps; ++s) {
+    const StepInfo si = step_info(s);
+    const int nu = num_units(s);
+    bool any_g2 = false;
+    for (int j = 0; j < nu; ++j) any_g2 = any_g2 || unit_info(s, j).group == 2;
+    for (int u = 0; u < nu; ++u, ++i) {
+      const UnitInfo ui = unit_info(s, u);
+      bool first_of_half = true, first_g1 = true, first_g2 = true;
+      for (int j = 0; j < u; ++j) {
+        const UnitInfo uj = unit_info(s, j);
+        if (uj.h == ui.h) first_of_half = false;
+        if (uj.group == 1) first_g1 = false;
+        if (uj.group == 2) first_g2 = false;
+      }
+      uint32_t flags = 0;
+      if (ui.from_pe) flags |= kUnitFromPe;
+      if (ui.group == 1 && first_g1) flags |= kUnitWait0;
+      if (ui.group == 2 && first_g2) flags |= kUnitWait1;
+      if (first_of_half) flags |= kUnitFirst;
+      if (ui.last) flags |= (ui.h ? kUnitCommit1 : kUnitCommit0);
+      if (ui.last && si.nh1 == 0) flags |= kUnitCommit1;             // single-half step releases both barriers
+      if (u == nu - 1 && !any_g2) flags |= kUnitPostWait1;           // still consume the half-1 "converted" signal
+      const uint32_t d_col = region_col_c(s) + ui.h * 128;
+      const uint32_t a_col = (region_col_c(s) ^ 256u) + (uint32_t)(ui.ka - si.pe_first) * 64u;
+      t.e[i].x = umma_idesc_f16(kTileM, ui.rows);
+      t.e[i].y = d_col | (a_col << 16);
+      t.e[i].z = flags;
+      t.e[i].w = (uint32_t)(step_offset_x1(s) + unit_offset_in_step(s, u)) | ((uint32_t)ui.rows << 24);
+    }
+  }
+  return t;
+}
+// Constant memory: the issue loops index it with a warp-uniform counter, so entries arrive in uniform registers
+// (ULDC) — which is where UTCHMMA / UBLKCP take their operands from.  (From shared memory every field needs an R2UR.)
+__constant__ ProgTable c_prog = make_prog();
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 struct RayP {  // per-ray constants in shared memory (kRayFloats floats)
@@ -253,6 +296,8 @@ __device__ __forceinline__ float composite_ray(const float4* __restrict__ pre, c
   return wl;
 }
 
+__device__ __forceinline__ uint32_t cta_rank_early() { return cluster_ctarank(); }
+
 // ------------------------------------------------------------------------------------------------
 template <bool EXACT>
 __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
@@ -274,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumSlots; ++i) {
       mbar_init(bar_full + i * 8, 1);
-      mbar_init(bar_empty + i * 8, 1);
+      mbar_init(bar_empty + i * 8, kCluster);  // released by the MMA warp of every CTA of the cluster
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar_aready + h * 8, kRowThreads / 32);  // one arrival per row warp per step
@@ -290,66 +335,43 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     bias_s[i] = p.bias[0][i];
     bias_s[kBiasFloats + i] = (p.nf > 0) ? p.bias[1][i] : 0.f;
   }
-  if (threadIdx.x < kTileUnits) {
-    int s = 0, u = threadIdx.x;
-    while (u >= num_units(s)) { u -= num_units(s); ++s; }
-    const StepInfo si = step_info(s);
-    const UnitInfo ui = unit_info(s, u);
-    bool first_of_half = true, first_g1 = true, first_g2 = true, any_g2 = false;
-    for (int j = 0; j < num_units(s); ++j) {
-      const UnitInfo uj = unit_info(s, j);
-      if (j < u && uj.h == ui.h) first_of_half = false;
-      if (j < u && uj.group == 1) first_g1 = false;
-      if (j < u && uj.group == 2) first_g2 = false;
-      if (uj.group == 2) any_g2 = true;
-    }
-    uint32_t flags = 0;
-    if (ui.from_pe) flags |= kUnitFromPe;
-    if (ui.group == 1 && first_g1) flags |= kUnitWait0;
-    if (ui.group == 2 && first_g2) flags |= kUnitWait1;
-    if (first_of_half) flags |= kUnitFirst;
-    if (ui.last) flags |= (ui.h ? kUnitCommit1 : kUnitCommit0);
-    if (ui.last && si.nh1 == 0) flags |= kUnitCommit1;                      // single-half step releases both barriers
-    if (u == num_units(s) - 1 && !any_g2) flags |= kUnitPostWait1;          // still consume the half-1 "converted" signal
-    const uint32_t d_col = region_col(s) + ui.h * 128;
-    const uint32_t a_col = (region_col(s) ^ 256u) + (uint32_t)(ui.ka - si.pe_first) * 64u;
-    uint4 e;
-    e.x = umma_idesc_f16(kTileM, ui.rows);
-    e.y = d_col | (a_col << 16);
-    e.z = flags;
-    e.w = (uint32_t)(step_offset_x1(s) + unit_offset_in_step(s, u)) | ((uint32_t)ui.rows << 24);
-    reinterpret_cast<uint4*>(smem + kOffProg)[threadIdx.x] = e;
-  }
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();  // peer barriers are initialised before anyone multicasts into them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_s;
-  const uint4* prog = reinterpret_cast<const uint4*>(smem + kOffProg);
+  const uint32_t cta_rank = cluster_ctarank();
+  constexpr uint16_t kAllCtas = (1u << kCluster) - 1;
 
-  const int n_iter = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Both CTAs of a cluster run the same number of iterations (they share the weight ring protocol); a CTA
+  // without a real unit in the last one renders invalid rays (no outputs).
+  const int first_in_cluster = (int)blockIdx.x - (int)cta_rank_early();
+  const int n_iter = (p.n_units - first_in_cluster + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tiles_per_unit = p.tiles_c + p.tiles_f;
 
   if (warp == 0) {
     // ============================== weight producer ==============================
     // The whole warp runs the (warp-uniform) loop; one elected lane issues the copies.
     {
-      uint32_t slot = 0, phase = 0;
+      uint32_t slot = 0, phase = 0, seq = 0;
       PhaseTimer tm(p.prof, p.prof != nullptr && lane == 0);
       for (int it = 0; it < n_iter; ++it) {
         for (int t = 0; t < tiles_per_unit; ++t) {
           const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
           for (int i = 0; i < kTileUnits; ++i) {
-            const uint32_t w = prog[i].w;
+            const uint32_t w = c_prog.e[i].w;
             const uint32_t off = w & 0xFFFFFFu, bytes = (w >> 24) * 128u;
 #pragma unroll
             for (int part = 0; part < NPART; ++part) {
               const uint8_t* src = EXACT ? base + 2 * (size_t)off + part * bytes : base + off;
-              mbar_wait(bar_empty + slot * 8, phase ^ 1);
+              mbar_wait(bar_empty + slot * 8, phase ^ 1);  // slot released in every CTA of the cluster
               if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
-                bulk_g2s(smem_base + kOffRing + slot * kMaxUnitBytes, src, bytes, bar_full + slot * 8);
+                if ((seq % kCluster) == cta_rank)  // the CTAs take turns loading; every copy lands in all of them
+                  bulk_g2s_multicast(smem_base + kOffRing + slot * kMaxUnitBytes, src, bytes, bar_full + slot * 8, kAllCtas);
               }
               __syncwarp();
+              ++seq;
               if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
             }
           }
@@ -363,12 +385,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     {
       uint32_t slot = 0, phase = 0, ph_a0 = 0, ph_a1 = 0;
       PhaseTimer tm(p.prof, p.prof != nullptr && lane == 0);
+      const bool prof_on = p.prof != nullptr;
+      long long acc_gate = 0, acc_full = 0, acc_issue = 0, tq = prof_on ? clock64() : 0;
       const uint64_t pe_desc_hi = umma_smem_desc_sw128(smem_base + kOffPeHi);
       const uint64_t pe_desc_lo = umma_smem_desc_sw128(smem_base + kOffPeLo);
       for (int it = 0; it < n_iter; ++it) {
         for (int t = 0; t < tiles_per_unit; ++t) {
           for (int i = 0; i < kTileUnits; ++i) {
-            const uint4 e = prog[i];
+            const ProgEntry e = c_prog.e[i];
+            if (prof_on) { const long long tn = clock64(); acc_issue += tn - tq; tq = tn; }
             if (e.z & kUnitWait0) {  // group-1 units: previous step's half-0 output (or the PE buffer) is in place
               mbar_wait(bar_aready, ph_a0);
               ph_a0 ^= 1;
@@ -379,12 +404,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               ph_a1 ^= 1;
               tc_fence_after_sync();
             }
+            if (prof_on) { const long long tn = clock64(); acc_gate += tn - tq; tq = tn; }
             const uint32_t d_tmem = tmem_base + (e.y & 0xFFFFu);
             const uint32_t a_tmem = tmem_base + (e.y >> 16);  // hi at +0, lo at +32 (2 fp16 per column)
             const uint32_t first = (e.z & kUnitFirst) ? 0u : 1u;
 #pragma unroll
             for (int part = 0; part < NPART; ++part) {
               mbar_wait(bar_full + slot * 8, phase);
+              if (prof_on) { const long long tn = clock64(); acc_full += tn - tq; tq = tn; }
               tc_fence_after_sync();
               const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + slot * kMaxUnitBytes);
               if (elect_one()) {
@@ -400,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                     if (EXACT && part == 0) umma_ts(d_tmem, a_tmem + 32 + ks * 8, bd, e.x, 1);
                   }
                 }
-                umma_commit(bar_empty + slot * 8);  // slot reusable once these MMAs have read it
+                umma_commit_multicast(bar_empty + slot * 8, kAllCtas);  // slot free here -> tell every loader
                 if (part == NPART - 1) {
                   if (e.z & kUnitCommit0) umma_commit(bar_accfull);      // half 0 complete -> its epilogue may start
                   if (e.z & kUnitCommit1) umma_commit(bar_accfull + 8);  // half 1 complete
@@ -414,8 +441,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               ph_a1 ^= 1;
             }
           }
-          tm.lap(44);
         }
+      }
+      if (prof_on && lane == 0) {
+        atomicAdd(p.prof + 44, (unsigned long long)acc_issue);
+        atomicAdd(p.prof + 45, (unsigned long long)acc_gate);
+        atomicAdd(p.prof + 46, (unsigned long long)acc_full);
       }
     }
   } else {
@@ -830,6 +861,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
   }
 
   __syncthreads();
+  cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers or write its ring
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
@@ -843,14 +875,25 @@ cudaError_t render_kernel_setup() {
 }
 
 cudaError_t launch_render(const RenderParams& p, int precision, int num_sms, cudaStream_t st, long long* launches) {
-  const int grid = p.n_units < num_sms ? p.n_units : num_sms;
+  int grid = p.n_units < num_sms ? p.n_units : num_sms;
   if (grid <= 0) return cudaSuccess;
-  if (precision == 1)
-    render_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
-  else
-    render_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(p);
+  grid = (grid + kCluster - 1) / kCluster * kCluster;        // whole clusters
+  if (grid > num_sms) grid = num_sms / kCluster * kCluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = (precision == 1) ? cudaLaunchKernelEx(&cfg, render_kernel<true>, p) : cudaLaunchKernelEx(&cfg, render_kernel<false>, p);
   ++*launches;
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace nfb
