@@ -221,7 +221,6 @@ int nfb_render_forward(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm,
   if (dbg) {
     p.dbg_z_c = dbg->z_coarse; p.dbg_raw_c = dbg->raw_coarse; p.dbg_z_f = dbg->z_fine; p.dbg_raw_f = dbg->raw_fine;
     p.dbg_act = dbg->act_dump; p.dbg_act_step = dbg->act_step; p.prof = dbg->prof;
-    if (!dbg->act_dump && dbg->act_step != -100) p.dbg_act_step = 0;
   }
   NFB_CUDA(nfb::launch_render(p, exact ? 1 : 0, h->num_sms, st, &h->launches));
   return NFB_OK;

@@ -19,12 +19,11 @@
 //   7,8   layers_dir.1,2             128                  128                        TMEM
 //   9     fc_rgb                     16 (3 used)          128                        TMEM
 //
-// Every step is issued as (up to) two N-halves with separate accumulators so that the epilogue of one half
-// overlaps the MMAs of the other and the next step can start on the K atoms that are already converted.
-// A weight "unit" = the rows of one half x one 64-wide K atom (<= 16 KB), in the order the MMA warp consumes them:
-//   [PE atom of half 0, of half 1] [hidden atoms 0,1 of half 0, of half 1]  |  [hidden atoms 2,3 of half 0, of half 1]
-//   `-------------------------- group 1 ---------------------------------'     `------------ group 2 -------------'
-// group 1 needs only what the half-0 epilogue of the previous step produced, group 2 also its half-1 epilogue.
+// A weight "unit" = all N rows of the step x one 64-wide K atom (<= 32 KB), consumed by 4 tcgen05.mma (M=128, N, K=16).
+// The epilogue converts the accumulator in two column halves ("half 0" = output columns [0,128) = K atoms 0,1 of the
+// next step, "half 1" = [128,256) = atoms 2,3) and signals each; the units of the next step are grouped by what they
+// need:   [PE atom] [hidden atoms 0,1] = group 1 (needs half 0 only)   |   [hidden atoms 2,3] = group 2 (needs half 1 too)
+// so the next step starts on atoms 0,1 while the second half of the previous step is still being converted.
 #pragma once
 #include <stdint.h>
 
@@ -39,7 +38,7 @@ namespace nfb {
 constexpr int kTileM = 128;      // rows (samples) per tensor-core tile == TMEM lanes
 constexpr int kAtomK = 64;       // fp16 elements per 128-byte swizzle row
 constexpr int kNumSteps = 10;
-constexpr int kMaxUnitBytes = 128 * 128;  // one weight unit: <=128 output rows x 64 K x 2 B
+constexpr int kMaxUnitBytes = 256 * 128;  // one weight unit: <=256 output rows x 64 K x 2 B
 constexpr int kDimXyz = 63, kDimDir = 24, kDimExpr = 76, kDimLatent = 32, kDimCond = 108;
 
 struct StepInfo {
@@ -85,28 +84,13 @@ struct UnitInfo {
   int16_t rows;     // output rows (MMA N) of the unit
   int16_t last;     // last unit of its half in this step (-> commit "accumulator half complete")
 };
-NFB_HD constexpr int num_units(int s) {
-  return step_info(s).k_atoms * (step_info(s).nh1 > 0 ? 2 : 1);
-}
+NFB_HD constexpr int num_units(int s) { return step_info(s).k_atoms; }
 NFB_HD constexpr UnitInfo unit_info(int s, int u) {
   const StepInfo si = step_info(s);
-  const int halves = si.nh1 > 0 ? 2 : 1;
-  const int hid = si.k_atoms - si.pe_first;          // hidden (TMEM) atoms: 0, 2 or 4
-  const int npe = si.pe_first ? halves : 0;
-  int h = 0, ka = 0, from_pe = 0, group = 1, last = 0;
-  if (u < npe) {
-    h = u; ka = 0; from_pe = 1; last = (hid == 0);
-  } else {
-    const int v = u - npe;
-    const int g1 = hid < 2 ? hid : 2;
-    if (v < g1 * halves) {
-      h = v / g1; ka = si.pe_first + v % g1; last = (hid <= 2 && v % g1 == g1 - 1);
-    } else {
-      const int w = v - g1 * halves;
-      h = w / 2; ka = si.pe_first + 2 + w % 2; group = 2; last = (w % 2 == 1);
-    }
-  }
-  return UnitInfo{(int16_t)h, (int16_t)ka, (int16_t)from_pe, (int16_t)group, (int16_t)(h ? si.nh1 : si.nh0), (int16_t)last};
+  const int hid = u - si.pe_first;  // hidden atom index (< 0: the PE atom)
+  const int group = (hid >= 2) ? 2 : 1;
+  return UnitInfo{0, (int16_t)u, (int16_t)(si.pe_first && u == 0), (int16_t)group, (int16_t)(si.nh0 + si.nh1),
+                  (int16_t)(u == si.k_atoms - 1)};
 }
 // Byte offset of unit u inside its step, x1 stream.
 NFB_HD constexpr int unit_offset_in_step(int s, int u) {

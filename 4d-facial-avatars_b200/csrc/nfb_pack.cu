@@ -137,7 +137,7 @@ cudaError_t launch_load_weights(NetBuffers& nb, const float* const params[26], c
   const int ld[kNumSteps] = {171, 256, 256, 427, 256, 256, 256, 128, 128, 128};
   const int nv[kNumSteps] = {256, 256, 256, 256, 256, 256, 129, 128, 128, 3};
   for (int s = 0; s < kNumSteps; ++s) {
-    pack_step_kernel<<<dim3(4, num_units(s)), 256, 0, st>>>(src[s], ld[s], nv[s], s, nb.stream_x1, nb.stream_x3);
+    pack_step_kernel<<<dim3(8, num_units(s)), 256, 0, st>>>(src[s], ld[s], nv[s], s, nb.stream_x1, nb.stream_x3);
     ++*launches;
   }
   return cudaGetLastError();

@@ -8,15 +8,15 @@
 //   volume_rendering_utils.py:7-75 volume_render_radiance_field
 //   models.py:236-261      ConditionalBlendshapePaperNeRFModel.forward
 //
-// Work decomposition.  A "unit" is R (1 or 2) rays.  One CTA per SM loops over units; per unit it runs
-// the coarse pass (R*Nc sample rows) and the fine pass (R*(Nc+Nf) rows) as 128-row tensor-core tiles.
-// Per tile the MLP is 10 GEMM steps (nfb_layout.h): accumulators live in TMEM, hidden activations are
-// written back to TMEM as FP16 (tcgen05.st) and consumed as the A operand of the next step straight
-// from TMEM, weights stream L2 -> shared memory through the bulk-copy (TMA) engine into an 8-slot ring
-// of pre-swizzled 16 KB units (one N-half x one 64-wide K atom), one tcgen05.mma (M=128, N<=128) per 16-wide K step.
-// Each step runs as two N-halves with their own accumulator and "done" barrier, and its units are ordered so that
-// the MMAs that only need the first half of the previous step's output are issued first: the epilogue of one half
-// overlaps the tensor-core work of the other half / the next step (nfb_layout.h).
+// Work decomposition.  A "unit of work" is R (1 or 2) rays.  One CTA per SM (clusters of 2 CTAs) loops over them;
+// per ray pair it runs the coarse pass (R*Nc sample rows) and the fine pass (R*(Nc+Nf) rows) as 128-row tensor-core tiles.
+// Per tile the MLP is 10 GEMM steps (nfb_layout.h).  TMEM holds two 256-column regions used alternately: step s
+// accumulates (FP32) into one while its A operand — the previous step's output, converted IN PLACE to FP16 by the
+// epilogue — is read from the other; hidden activations never leave TMEM.  Weights stream L2 -> shared memory through
+// the bulk-copy (TMA) engine into a 4-slot ring of pre-swizzled 32 KB units ([N rows x 64 K]); the two CTAs of a
+// cluster take turns issuing each copy as a cluster multicast, so every weight byte is read from L2 once per SM pair.
+// The epilogue converts and signals the accumulator in two column halves, and the units of the next step are ordered
+// so that the MMAs needing only the first half are issued while the second half is still being converted.
 //
 // Warp roles (320 threads): warp 0 = weight producer, warp 1 = tcgen05.mma issuer (also owns the TMEM
 // allocation), warps 2..9 = "row" warps.  A row warp may only touch the TMEM lane quadrant (warp & 3), so
@@ -33,7 +33,7 @@
 
 namespace nfb {
 
-constexpr int kNumSlots = 8;    // ring of 16 KB weight units
+constexpr int kNumSlots = 4;    // ring of 32 KB weight units
 constexpr int kRowsMax = 1024;  // sample rows of one pass of one unit
 constexpr int kThreads = 320;   // producer warp + MMA warp + 8 row warps
 constexpr int kCluster = 2;     // CTAs (SMs) per cluster sharing every weight unit through one multicast L2 read
@@ -64,14 +64,13 @@ constexpr int kOffRay = kOffDirBias + 2 * 128 * 4;
 constexpr int kOffBars = kOffRay + 2 * kRayFloats * 4;
 constexpr int kNumBars = 2 * kNumSlots + 4;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
-constexpr int kMaxProg = 80;                     // weight units per tile (74 with the current step table)
-constexpr int kOffProg = kOffTmemPtr + 16;       // uint4 per unit: the MMA warp's and the producer's "program"
-constexpr int kSmemBytes = kOffProg + kMaxProg * 16;
-static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0 && kOffProg % 16 == 0, "alignment");
+constexpr int kMaxProg = 40;                     // weight units per tile (32 with the current step table)
+constexpr int kSmemBytes = kOffTmemPtr + 16;
+static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0, "alignment");
 
-// Per-unit program entry, built once per CTA (the step/unit tables of nfb_layout.h involve divisions that are far too
-// slow for the single-lane issue loops):  x = instruction descriptor, y = accumulator column | A column << 16 (TMEM columns
-// relative to the allocation base), z = flags, w = byte offset in the x1 weight stream | rows << 24.
+// Per-unit program entry, precomputed at compile time (the step/unit tables of nfb_layout.h involve divisions that are
+// far too slow for the issue loops):  x = instruction descriptor, y = accumulator column | A column << 16 (TMEM columns
+// relative to the allocation base), z = flags, w = (byte offset in the x1 weight stream) / 16 | rows << 20.
 enum : uint32_t {
   kUnitFromPe = 1u, kUnitWait0 = 2u, kUnitWait1 = 4u, kUnitFirst = 8u, kUnitCommit0 = 16u, kUnitCommit1 = 32u, kUnitPostWait1 = 64u
 };
@@ -108,15 +107,14 @@ constexpr ProgTable make_prog() {
       if (ui.group == 1 && first_g1) flags |= kUnitWait0;
       if (ui.group == 2 && first_g2) flags |= kUnitWait1;
       if (first_of_half) flags |= kUnitFirst;
-      if (ui.last) flags |= (ui.h ? kUnitCommit1 : kUnitCommit0);
-      if (ui.last && si.nh1 == 0) flags |= kUnitCommit1;             // single-half step releases both barriers
+      if (ui.last) flags |= kUnitCommit0;                               // the step's accumulator is complete
       if (u == nu - 1 && !any_g2) flags |= kUnitPostWait1;           // still consume the half-1 "converted" signal
-      const uint32_t d_col = region_col_c(s) + ui.h * 128;
+      const uint32_t d_col = region_col_c(s);
       const uint32_t a_col = (region_col_c(s) ^ 256u) + (uint32_t)(ui.ka - si.pe_first) * 64u;
       t.e[i].x = umma_idesc_f16(kTileM, ui.rows);
       t.e[i].y = d_col | (a_col << 16);
       t.e[i].z = flags;
-      t.e[i].w = (uint32_t)(step_offset_x1(s) + unit_offset_in_step(s, u)) | ((uint32_t)ui.rows << 24);
+      t.e[i].w = ((uint32_t)(step_offset_x1(s) + unit_offset_in_step(s, u)) >> 4) | ((uint32_t)ui.rows << 20);  // rows <= 256
     }
   }
   return t;
@@ -137,10 +135,6 @@ struct RayP {  // per-ray constants in shared memory (kRayFloats floats)
   float pad[3];
 };
 static_assert(sizeof(RayP) == kRayFloats * 4, "RayP size");
-
-__device__ const int kStepOff[kNumSteps] = {step_offset_x1(0), step_offset_x1(1), step_offset_x1(2), step_offset_x1(3),
-                                            step_offset_x1(4), step_offset_x1(5), step_offset_x1(6), step_offset_x1(7),
-                                            step_offset_x1(8), step_offset_x1(9)};
 
 // ------------------------------------------------------------------------------------------------
 // sin/cos of y for the positional encoding.  The reference evaluates torch.sin(x * 2^k) in FP32
@@ -360,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
           for (int i = 0; i < kTileUnits; ++i) {
             const uint32_t w = c_prog.e[i].w;
-            const uint32_t off = w & 0xFFFFFFu, bytes = (w >> 24) * 128u;
+            const uint32_t off = (w & 0xFFFFFu) << 4, bytes = (w >> 20) * 128u;
 #pragma unroll
             for (int part = 0; part < NPART; ++part) {
               const uint8_t* src = EXACT ? base + 2 * (size_t)off + part * bytes : base + off;
@@ -469,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     RayP* rayp = reinterpret_cast<RayP*>(smem + kOffRay);
     const int R = p.rays_per_unit;
     const bool has_bg = p.bg != nullptr;
-    uint32_t ph_acc0 = 0, ph_acc1 = 0;
+    uint32_t ph_acc0 = 0;
     PhaseTimer tm(p.prof, p.prof != nullptr && etid == 0);
 
     for (int it = 0; it < n_iter; ++it) {
@@ -654,9 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             ph_acc0 ^= 1;
             tc_fence_after_sync();
             tm.lap(10 + s);
-            const bool skip_epi = (p.dbg_act_step == -100);  // timing experiment: tensor-core side alone
-            if (skip_epi) {
-            } else if (s <= 8) {  // ReLU layers: this thread converts output columns [64*ch, 64*ch+64) of the half in place
+            if (s <= 8) {  // ReLU layers: this thread converts output columns [64*ch, 64*ch+64) of the half in place
               const int c0 = 64 * ch;
               if (s == 6 && t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias written by all threads
               const uint32_t extra = (s == 6) ? smem_u32(dirbias + r * 128 + c0) : 0u;
@@ -700,13 +692,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               if (lane == 0) mbar_arrive(bar_aready);
             }
             tm.lap(20 + s);
-            // ---------------- half 1
-            mbar_wait(bar_accfull + 8, ph_acc1);
-            ph_acc1 ^= 1;
-            tc_fence_after_sync();
+            // ---------------- half 1 (same accumulator, columns [128,256))
             tm.lap(30 + (s < 8 ? s : 7));
-            if (skip_epi) {
-            } else if (s <= 5) {
+            if (s <= 5) {
               const int c0 = 128 + 64 * ch;
               epi_half<EXACT>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), 0u, dump ? dump + c0 : nullptr);
             } else if (s == 6 && ch == 0) {  // sigma = first column of half 1 of the folded layers_dir.0 | fc_alpha step

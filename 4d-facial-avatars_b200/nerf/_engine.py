@@ -198,8 +198,6 @@ class Renderer:
         if prof is not None:  # int64[64] CUDA tensor of phase-cycle counters
             dbg = capi.NfbDebug()
             dbg.prof = prof.data_ptr()
-            if os.environ.get("NFB_SKIP_EPILOGUE"):  # timing experiment (results are garbage)
-                dbg.act_step = -100
         capi.check(capi.lib.nfb_render_forward(self._h, C.byref(rays), C.byref(sm), None, C.byref(o),
                                                C.byref(dbg) if dbg is not None else None, _stream()), "render_forward")
         views["_buf"] = out
