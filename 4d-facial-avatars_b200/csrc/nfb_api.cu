@@ -162,7 +162,7 @@ int nfb_render_forward(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm,
   if ((rays->o == nullptr) != (rays->d == nullptr)) return NFB_ERR_INVALID;
   if (!rays->o && (rays->width <= 0 || rays->height <= 0)) return NFB_ERR_INVALID;
   const int nc = sm->num_coarse, nf = sm->num_fine;
-  if (nc < 3 || nf < 0 || nc + nf > 1024) return NFB_ERR_UNSUPPORTED;
+  if (nc < 3 || nf < 0 || nc + nf > 512) return NFB_ERR_UNSUPPORTED;
   if (sm->lindisp) return NFB_ERR_UNSUPPORTED;
   if (sm->precision != NFB_PREC_FAST && sm->precision != NFB_PREC_EXACT) return NFB_ERR_INVALID;
   if (!h->net[0].loaded || (nf > 0 && !h->net[1].loaded) || !h->frame_set) return NFB_ERR_STATE;
@@ -187,7 +187,7 @@ int nfb_render_forward(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm,
   p.near_ = rays->near_; p.far_ = rays->far_;
   p.dir_z = rays->dir_z; p.bg = rays->background;
   p.nc = nc; p.nf = nf; p.s_fine = nc + nf;
-  p.rays_per_unit = (2 * (nc + nf) <= 1024) ? 2 : 1;
+  p.rays_per_unit = (2 * (nc + nf) <= 512) ? 2 : 1;
   p.tiles_c = (p.rays_per_unit * nc + 127) / 128;
   p.tiles_f = nf > 0 ? (p.rays_per_unit * (nc + nf) + 127) / 128 : 0;
   p.n_units = (rays->n_rays + p.rays_per_unit - 1) / p.rays_per_unit;

@@ -33,10 +33,13 @@
 
 namespace nfb {
 
-constexpr int kNumSlots = 4;    // ring of 32 KB weight units
-constexpr int kRowsMax = 1024;  // sample rows of one pass of one unit
+constexpr int kNumSlots = 5;    // ring of 32 KB weight units (exact mode uses 4: slot 4 holds the lo half of the PE operand)
+constexpr int kRowsMax = 512;   // sample rows of one pass of one unit of work
 constexpr int kThreads = 320;   // producer warp + MMA warp + 8 row warps
-constexpr int kCluster = 2;     // CTAs (SMs) per cluster sharing every weight unit through one multicast L2 read
+#ifndef NFB_CLUSTER
+#define NFB_CLUSTER 2
+#endif
+constexpr int kCluster = NFB_CLUSTER;  // CTAs (SMs) per cluster sharing every weight unit through one multicast L2 read
 constexpr int kRowThreads = 256;
 constexpr uint32_t kRowBarrier = 1;  // named barrier id of the four row warps
 
@@ -50,8 +53,8 @@ __device__ __forceinline__ uint32_t region_col(int s) { return (s & 1) ? 256u : 
 // shared memory map (bytes from the 1024-aligned base)
 constexpr int kOffRing = 0;
 constexpr int kOffPeHi = kOffRing + kNumSlots * kMaxUnitBytes;
-constexpr int kOffPeLo = kOffPeHi + kTileM * 128;
-constexpr int kOffBias = kOffPeLo + kTileM * 128;
+constexpr int kOffPeLo = kOffRing + (kNumSlots - 1) * kMaxUnitBytes;  // exact mode only: inside the last ring slot
+constexpr int kOffBias = kOffPeHi + kTileM * 128;
 constexpr int kOffRaw = kOffBias + 2 * kBiasFloats * 4;
 constexpr int kOffZ = kOffRaw + kRowsMax * 16;
 constexpr int kOffW = kOffZ + kRowsMax * 4;
@@ -302,6 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
   if ((smem_base & 1023u) != 0u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NPART = EXACT ? 2 : 1;
+  constexpr uint32_t NSLOT = EXACT ? kNumSlots - 1 : kNumSlots;
 
   const uint32_t bar_full = smem_base + kOffBars;               // [kNumSlots]
   const uint32_t bar_empty = bar_full + kNumSlots * 8;          // [kNumSlots]
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               }
               __syncwarp();
               ++seq;
-              if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+              if (++slot == NSLOT) { slot = 0; phase ^= 1; }
             }
           }
           tm.lap(41);
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                 }
               }
               __syncwarp();
-              if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+              if (++slot == NSLOT) { slot = 0; phase ^= 1; }
             }
             if (e.z & kUnitPostWait1) {
               mbar_wait(bar_aready + 8, ph_a1);

@@ -4,15 +4,14 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnfb.so")
+LIB_PATH = os.environ.get("NFB_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libnfb.so")
 
 NFB_OK = 0
 NFB_NET_COARSE, NFB_NET_FINE = 0, 1
 NFB_PREC_FAST, NFB_PREC_EXACT = 0, 1
 
 EXPORTS = ["nfb_version", "nfb_strerror", "nfb_last_cuda_error", "nfb_create", "nfb_destroy", "nfb_load_weights",
-           "nfb_set_frame", "nfb_render_forward", "nfb_render_backward", "nfb_render_frame_host", "nfb_launch_count",
-           "nfb_host_linspace"]
+           "nfb_set_frame", "nfb_render_forward", "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace"]
 
 
 class NfbModelDims(C.Structure):
@@ -46,10 +45,6 @@ class NfbDebug(C.Structure):
                 ("act_dump", C.c_void_p), ("act_step", C.c_int32), ("prof", C.c_void_p)]
 
 
-class NfbOutGrads(C.Structure):
-    _fields_ = [("d_rgb_coarse", C.c_void_p), ("d_rgb_fine", C.c_void_p)]
-
-
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} not found: build it with `python 4d-facial-avatars_b200/build.py` "
@@ -70,9 +65,6 @@ def _load():
                                           C.POINTER(NfbSampling), C.c_void_p, C.c_void_p]
     lib.nfb_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     lib.nfb_host_linspace.argtypes = [C.POINTER(C.c_float), C.c_int]
-    if hasattr(lib, "nfb_render_backward"):
-        lib.nfb_render_backward.argtypes = [C.c_void_p, C.POINTER(NfbRays), C.POINTER(NfbSampling), C.POINTER(NfbNoise),
-                                            C.POINTER(NfbDebug), C.POINTER(NfbOutGrads), C.c_void_p, C.c_void_p]
     for fn in ("nfb_create", "nfb_destroy", "nfb_load_weights", "nfb_set_frame", "nfb_render_forward",
                "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace"):
         getattr(lib, fn).restype = C.c_int
