@@ -41,7 +41,32 @@ struct NfbHandle {
   // staging for nfb_render_frame_host
   float *d_expr = nullptr, *d_latent = nullptr, *d_bg = nullptr, *d_out = nullptr;
   size_t bg_cap = 0, out_cap = 0;
+  // training state: what nfb_render_forward_train saved for nfb_render_backward (grow-only buffers)
+  struct Train {
+    uint8_t* rec = nullptr; size_t rec_tiles = 0;       // per-tile activation records (nfb_layout.h kRec*)
+    float* draw = nullptr; size_t draw_tiles = 0;       // [tiles][128][4]
+    float *z_c = nullptr, *raw_c = nullptr, *z_f = nullptr, *raw_f = nullptr, *dnorm = nullptr;
+    size_t cap_zc = 0, cap_rawc = 0, cap_zf = 0, cap_rawf = 0, cap_dn = 0;
+    float* acc[2] = {nullptr, nullptr};                 // kAccFloats each
+    float* scal = nullptr;                              // [0] scale, [1] 1/scale, [2] max |d raw| (bits)
+    int n_rays = 0, nc = 0, nf = 0, rays_per_unit = 0, tiles_c = 0, tiles_f = 0, n_units = 0, has_bg = 0, white_bkgd = 0;
+    bool valid = false;
+  } tr;
+  float* cond = nullptr;  // [108] = [expression / 3 ; latent] of the current frame
 };
+
+namespace {
+template <class T>
+int ensure_cap(T** p, size_t* cap, size_t n) {
+  if (*cap >= n && *p) return NFB_OK;
+  if (*p) NFB_CUDA(cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  *cap = n;
+  return NFB_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -96,7 +121,12 @@ int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
     NFB_CUDA(dev_alloc(&nb.w0c, 256 * nfb::kDimCond));
     NFB_CUDA(dev_alloc(&nb.w3c, 256 * nfb::kDimCond));
     NFB_CUDA(dev_alloc(&nb.wd0b_t, nfb::kDimDir * 128));
+    NFB_CUDA(dev_alloc(&nb.stream_bwd, nfb::kBwdStreamBytes));
+    NFB_CUDA(dev_alloc(&h->tr.acc[n], nfb::kAccFloats));
   }
+  NFB_CUDA(dev_alloc(&h->tr.scal, 4));
+  NFB_CUDA(dev_alloc(&h->cond, nfb::kDimCond));
+  NFB_CUDA(nfb::train_kernels_setup());
   NFB_CUDA(dev_alloc(&h->d_expr, nfb::kDimExpr));
   NFB_CUDA(dev_alloc(&h->d_latent, nfb::kDimLatent));
   NFB_CUDA(nfb::render_kernel_setup());
@@ -110,8 +140,11 @@ int nfb_destroy(NfbHandle* h) {
   for (int n = 0; n < 2; ++n) {
     nfb::NetBuffers& nb = h->net[n];
     cudaFree(nb.stream_x1); cudaFree(nb.stream_x3); cudaFree(nb.w6); cudaFree(nb.b6); cudaFree(nb.bias_static);
-    cudaFree(nb.bias_frame); cudaFree(nb.w0c); cudaFree(nb.w3c); cudaFree(nb.wd0b_t);
+    cudaFree(nb.bias_frame); cudaFree(nb.w0c); cudaFree(nb.w3c); cudaFree(nb.wd0b_t); cudaFree(nb.stream_bwd);
+    cudaFree(h->tr.acc[n]);
   }
+  cudaFree(h->tr.rec); cudaFree(h->tr.draw); cudaFree(h->tr.z_c); cudaFree(h->tr.raw_c); cudaFree(h->tr.z_f); cudaFree(h->tr.raw_f);
+  cudaFree(h->tr.dnorm); cudaFree(h->tr.scal); cudaFree(h->cond);
   cudaFree(h->lin_c); cudaFree(h->lin_f); cudaFree(h->d_expr); cudaFree(h->d_latent); cudaFree(h->d_bg); cudaFree(h->d_out);
   delete h;
   return NFB_OK;
@@ -125,6 +158,7 @@ int nfb_load_weights(NfbHandle* h, int which, const float* const params[26], voi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   nfb::NetBuffers& nb = h->net[which];
   NFB_CUDA(nfb::launch_load_weights(nb, params, st, &h->launches));
+  NFB_CUDA(nfb::launch_pack_bwd(nb, params, st, &h->launches));  // transposed stream for the backward chain
   nb.loaded = true;
   h->frame_set = false;  // folded biases are stale
   return NFB_OK;
@@ -137,6 +171,7 @@ int nfb_set_frame(NfbHandle* h, const float* expression, const float* latent, vo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int n = 0; n < 2; ++n)
     if (h->net[n].loaded) NFB_CUDA(nfb::launch_frame_fold(h->net[n], expression, latent, st, &h->launches));
+  NFB_CUDA(nfb::launch_cond(expression, latent, h->cond, st, &h->launches));
   h->frame_set = true;
   return NFB_OK;
 }
@@ -155,8 +190,8 @@ static int ensure_linspace(float** buf, int* cached_n, int n, cudaStream_t st) {
   return NFB_OK;
 }
 
-int nfb_render_forward(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm, const NfbNoise* noise, const NfbOutputs* out,
-                       const NfbDebug* dbg, void* stream) {
+static int render_impl(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm, const NfbNoise* noise, const NfbOutputs* out,
+                       const NfbDebug* dbg, void* stream, bool train) {
   if (!h || !rays || !sm || !out) return NFB_ERR_INVALID;
   if (rays->n_rays < 0) return NFB_ERR_INVALID;
   if ((rays->o == nullptr) != (rays->d == nullptr)) return NFB_ERR_INVALID;
@@ -222,7 +257,102 @@ int nfb_render_forward(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm,
     p.dbg_z_c = dbg->z_coarse; p.dbg_raw_c = dbg->raw_coarse; p.dbg_z_f = dbg->z_fine; p.dbg_raw_f = dbg->raw_fine;
     p.dbg_act = dbg->act_dump; p.dbg_act_step = dbg->act_step; p.prof = dbg->prof;
   }
+  if (train) {
+    // Saved for nfb_render_backward: per-tile activation records, sample depths, (colour, ReLU input of sigma), |d|.
+    NfbHandle::Train& tr = h->tr;
+    tr.valid = false;
+    const size_t n = (size_t)rays->n_rays, tiles = (size_t)p.n_units * (p.tiles_c + p.tiles_f);
+    int rc;
+    if ((rc = ensure_cap(&tr.rec, &tr.rec_tiles, tiles * nfb::kRecBytes))) return rc;
+    if ((rc = ensure_cap(&tr.draw, &tr.draw_tiles, tiles * 512))) return rc;
+    if ((rc = ensure_cap(&tr.z_c, &tr.cap_zc, n * nc))) return rc;
+    if ((rc = ensure_cap(&tr.raw_c, &tr.cap_rawc, n * nc * 4))) return rc;
+    if ((rc = ensure_cap(&tr.dnorm, &tr.cap_dn, n))) return rc;
+    if (nf > 0) {
+      if ((rc = ensure_cap(&tr.z_f, &tr.cap_zf, n * (nc + nf)))) return rc;
+      if ((rc = ensure_cap(&tr.raw_f, &tr.cap_rawf, n * (nc + nf) * 4))) return rc;
+    }
+    p.save_rec = tr.rec; p.save_dnorm = tr.dnorm; p.save_raw_c = tr.raw_c; p.save_raw_f = tr.raw_f;
+    p.dbg_z_c = tr.z_c; p.dbg_z_f = tr.z_f;
+    tr.n_rays = rays->n_rays; tr.nc = nc; tr.nf = nf; tr.rays_per_unit = p.rays_per_unit; tr.tiles_c = p.tiles_c;
+    tr.tiles_f = p.tiles_f; tr.n_units = p.n_units; tr.has_bg = rays->background != nullptr; tr.white_bkgd = p.white_bkgd;
+  }
   NFB_CUDA(nfb::launch_render(p, exact ? 1 : 0, h->num_sms, st, &h->launches));
+  if (train) h->tr.valid = true;
+  return NFB_OK;
+}
+
+int nfb_render_forward(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm, const NfbNoise* noise, const NfbOutputs* out,
+                       const NfbDebug* dbg, void* stream) {
+  return render_impl(h, rays, sm, noise, out, dbg, stream, false);
+}
+
+int nfb_render_forward_train(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm, const NfbNoise* noise,
+                             const NfbOutputs* out, void* stream) {
+  return render_impl(h, rays, sm, noise, out, nullptr, stream, true);
+}
+
+int nfb_render_backward(NfbHandle* h, const NfbOutGrads* og, const float* const params_coarse[26],
+                        const float* const params_fine[26], float* const grads_coarse[26], float* const grads_fine[26],
+                        float* grad_latent, void* stream) {
+  if (!h || !og || !params_coarse || !grads_coarse) return NFB_ERR_INVALID;
+  NfbHandle::Train& tr = h->tr;
+  if (!tr.valid) return NFB_ERR_STATE;
+  const bool fine = tr.nf > 0;
+  if (fine && (!params_fine || !grads_fine)) return NFB_ERR_INVALID;
+  for (int i = 0; i < 26; ++i) {
+    if (!params_coarse[i] || (fine && !params_fine[i])) return NFB_ERR_INVALID;
+    if (i != 22 && i != 23 && (!grads_coarse[i] || (fine && !grads_fine[i]))) return NFB_ERR_INVALID;
+  }
+  NFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t tiles = (size_t)tr.n_units * (tr.tiles_c + tr.tiles_f);
+  NFB_CUDA(cudaMemsetAsync(tr.draw, 0, tiles * 512 * sizeof(float), st));
+  NFB_CUDA(cudaMemsetAsync(tr.acc[0], 0, nfb::kAccFloats * sizeof(float), st));
+  NFB_CUDA(cudaMemsetAsync(tr.acc[1], 0, nfb::kAccFloats * sizeof(float), st));
+  NFB_CUDA(cudaMemsetAsync(tr.scal, 0, 4 * sizeof(float), st));
+
+  nfb::CompBwdParams q;
+  std::memset(&q, 0, sizeof(q));
+  q.n_rays = tr.n_rays; q.nc = tr.nc; q.nf = tr.nf; q.s_fine = tr.nc + tr.nf; q.rays_per_unit = tr.rays_per_unit;
+  q.tiles_c = tr.tiles_c; q.tiles_f = tr.tiles_f; q.has_bg = tr.has_bg; q.white_bkgd = tr.white_bkgd;
+  q.z_c = tr.z_c; q.raw_c = tr.raw_c; q.z_f = tr.z_f; q.raw_f = tr.raw_f; q.dnorm = tr.dnorm;
+  q.g_rgb[0] = og->rgb_coarse; q.g_disp[0] = og->disp_coarse; q.g_acc[0] = og->acc_coarse;
+  q.g_rgb[1] = og->rgb_fine; q.g_disp[1] = og->disp_fine; q.g_acc[1] = og->acc_fine; q.g_wlast = og->w_last;
+  q.draw = tr.draw; q.acc[0] = tr.acc[0]; q.acc[1] = tr.acc[1];
+  q.absmax = reinterpret_cast<unsigned int*>(tr.scal + 2);
+  NFB_CUDA(nfb::launch_composite_bwd(q, tr.scal, st, &h->launches));
+
+  nfb::ChainParams c;
+  c.n_units = tr.n_units; c.tiles_c = tr.tiles_c; c.tiles_f = tr.tiles_f;
+  c.rec = tr.rec; c.draw = tr.draw; c.scal = tr.scal;
+  c.wstream[0] = h->net[0].stream_bwd;
+  c.wstream[1] = fine ? h->net[1].stream_bwd : h->net[0].stream_bwd;
+  NFB_CUDA(nfb::launch_chain(c, h->num_sms, st, &h->launches));
+
+  for (int net = 0; net < (fine ? 2 : 1); ++net) {
+    nfb::DwParams d;
+    d.rec = tr.rec; d.n_units = tr.n_units; d.tpu = tr.tiles_c + tr.tiles_f;
+    d.t_base = net ? tr.tiles_c : 0; d.t_cnt = net ? tr.tiles_f : tr.tiles_c;
+    d.acc = tr.acc[net]; d.scal = tr.scal;
+    NFB_CUDA(nfb::launch_dw(d, h->num_sms, st, &h->launches));
+    NFB_CUDA(nfb::launch_finalize(net ? params_fine : params_coarse, net ? grads_fine : grads_coarse, tr.acc[net], h->cond, st,
+                                  &h->launches));
+  }
+  if (grad_latent)
+    NFB_CUDA(nfb::launch_latent_grad(params_coarse, fine ? params_fine : nullptr, tr.acc[0], tr.acc[1], grad_latent, st,
+                                     &h->launches));
+  return NFB_OK;
+}
+
+int nfb_train_debug(NfbHandle* h, NfbTrainDebug* out) {
+  if (!h || !out) return NFB_ERR_INVALID;
+  if (!h->tr.valid) return NFB_ERR_STATE;
+  const NfbHandle::Train& tr = h->tr;
+  out->records = tr.rec; out->n_tiles = (long long)tr.n_units * (tr.tiles_c + tr.tiles_f); out->record_bytes = nfb::kRecBytes;
+  out->d_raw = tr.draw; out->acc_coarse = tr.acc[0]; out->acc_fine = tr.acc[1]; out->acc_floats = nfb::kAccFloats;
+  out->scale = tr.scal; out->z_coarse = tr.z_c; out->raw_coarse = tr.raw_c; out->z_fine = tr.z_f; out->raw_fine = tr.raw_f;
+  out->tiles_coarse = tr.tiles_c; out->tiles_fine = tr.tiles_f; out->rays_per_unit = tr.rays_per_unit;
   return NFB_OK;
 }
 

@@ -17,6 +17,7 @@ struct NetBuffers {
   float* w0c = nullptr;          // [256,108] conditioning columns of layers_xyz.0
   float* w3c = nullptr;          // [256,108] conditioning columns of layers_xyz.3
   float* wd0b_t = nullptr;       // [24,128] direction columns of layers_dir.0, transposed
+  uint8_t* stream_bwd = nullptr; // kBwdStreamBytes: transposed FP16 weights for the backward chain (nfb_train.cu)
   bool loaded = false;
 };
 
@@ -49,11 +50,49 @@ struct RenderParams {
   const float* wd0b_t[2];
   // outputs
   float *rgb_c, *disp_c, *acc_c, *rgb_f, *disp_f, *acc_f, *w_last;
+  // training forward (all null in evaluation): per-tile activation records (nfb_layout.h kRec*), per-ray |d|, and per
+  // sample (colour or bg, ReLU input of sigma) of both passes
+  uint8_t* save_rec;
+  float* save_dnorm;
+  float *save_raw_c, *save_raw_f;
   // debug
   float *dbg_z_c, *dbg_raw_c, *dbg_z_f, *dbg_raw_f, *dbg_act;
   int dbg_act_step;
   unsigned long long* prof;  // optional [64] phase-cycle counters (see PhaseTimer in nfb_render.cu)
 };
+
+// ---- training (nfb_train.cu)
+struct CompBwdParams {
+  int n_rays, nc, nf, s_fine, rays_per_unit, tiles_c, tiles_f, has_bg, white_bkgd;
+  const float *z_c, *raw_c, *z_f, *raw_f, *dnorm;                       // saved by the training forward
+  const float *g_rgb[2], *g_disp[2], *g_acc[2], *g_wlast;               // dL/d outputs (coarse, fine); any may be null
+  float* draw;                                                          // [tiles][128][4] dL/d(rgb_raw, sigma_raw), zero-initialised
+  float* acc[2];                                                        // per-network accumulators (kAccBRaw sums land here)
+  unsigned int* absmax;                                                 // max |d raw| as float bits
+};
+struct ChainParams {
+  int n_units, tiles_c, tiles_f;
+  uint8_t* rec;
+  const float* draw;
+  const float* scal;            // [0] = loss scale, [1] = 1 / scale
+  const uint8_t* wstream[2];    // backward weight streams (coarse, fine)
+};
+struct DwParams {
+  const uint8_t* rec;
+  int n_units, tpu, t_base, t_cnt;  // tiles of this network: unit * tpu + t_base + [0, t_cnt)
+  float* acc;
+  const float* scal;
+};
+cudaError_t train_kernels_setup();
+cudaError_t launch_pack_bwd(NetBuffers& nb, const float* const params[26], cudaStream_t st, long long* launches);
+cudaError_t launch_cond(const float* expr, const float* latent, float* cond, cudaStream_t st, long long* launches);
+cudaError_t launch_composite_bwd(const CompBwdParams& q, float* scal, cudaStream_t st, long long* launches);
+cudaError_t launch_chain(const ChainParams& p, int num_sms, cudaStream_t st, long long* launches);
+cudaError_t launch_dw(const DwParams& p, int num_sms, cudaStream_t st, long long* launches);
+cudaError_t launch_finalize(const float* const params[26], float* const grads[26], const float* acc, const float* cond,
+                            cudaStream_t st, long long* launches);
+cudaError_t launch_latent_grad(const float* const params_c[26], const float* const params_f[26], const float* acc_c,
+                               const float* acc_f, float* out, cudaStream_t st, long long* launches);
 
 cudaError_t launch_load_weights(NetBuffers& nb, const float* const params[26], cudaStream_t st, long long* launches);
 cudaError_t launch_frame_fold(NetBuffers& nb, const float* expr, const float* latent, cudaStream_t st, long long* launches);

@@ -102,6 +102,71 @@ NFB_HD constexpr int unit_offset_in_step(int s, int u) {
 // XORed with (row & 7) — the SWIZZLE_128B pattern the UMMA shared-memory descriptor expects.
 NFB_HD constexpr int sw128_offset(int n, int k) { return n * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + ((k & 7) << 1); }
 
+
+// ------------------------------------------------------------------------------------------------
+// Training: per-tile activation record (written by the forward kernel in SAVE mode and by the backward chain kernel,
+// read by the weight-gradient kernel).  Every entry is a TRANSPOSED image of a [128 sample rows x C features] FP16
+// matrix: element (feature k, sample r) lives in r-atom (r >> 6) — a [C rows x 64 r] block in the same 128-byte-swizzled
+// K-major layout as a weight unit — so the weight-gradient GEMM  dW[n,k] = sum_r dY[r,n] X[r,k]  reads both operands
+// with plain bulk copies and the K-major descriptors of the forward pass (reduction dimension = sample rows).
+constexpr int kRecPE = 0;                         // positional encoding, 64 features (lane 63 = 0)
+constexpr int kRecH0 = 16384;                     // h0..h5 (outputs of tensor-core steps 0..5), 256 features each
+constexpr int kRecG0 = kRecH0 + 6 * 65536;        // g0..g2 (steps 6..8), 128 features each
+constexpr int kRecPEd = kRecG0 + 3 * 32768;       // per-ray direction encoding replicated per sample, 32 rows (24 used)
+constexpr int kRecMask = kRecPEd + 8192;          // ReLU masks: [9 layers][128 rows][8 x u32]
+constexpr int kRecDY0 = kRecMask + 9 * 128 * 32;  // dY0..dY5 (gradient w.r.t. the pre-activation of steps 0..5), 256 features
+constexpr int kRecDY6 = kRecDY0 + 6 * 65536;      // dY6..dY8, 128 features
+constexpr int kRecDRaw = kRecDY6 + 3 * 32768;     // scaled (d rgb_raw[3], d sigma_raw) image, 16 rows (4 used)
+constexpr int kRecBytes = kRecDRaw + 4096;
+static_assert(kRecBytes == (1 << 20), "tile record is 1 MiB");
+NFB_HD constexpr int rec_x_off(int layer) { return layer < 6 ? kRecH0 + layer * 65536 : kRecG0 + (layer - 6) * 32768; }
+NFB_HD constexpr int rec_dy_off(int layer) { return layer < 6 ? kRecDY0 + layer * 65536 : kRecDY6 + (layer - 6) * 32768; }
+NFB_HD constexpr int rec_width(int layer) { return layer < 6 ? 256 : 128; }
+// Byte offset of element (feature k, sample row r) inside an image with `rows` features.
+NFB_HD constexpr int img_offset(int rows, int k, int r) { return (r >> 6) * rows * 128 + sw128_offset(k, r & 63); }
+
+// Backward chain (dX): 9 tensor-core steps per 128-row tile, same machinery as the forward pass with transposed weights.
+//   step  computes                         N (half0+half1)  K atoms                A operand
+//   0     d g2 = d rgb . Wrgb              128              1 (smem, k<3 used)     SMEM (d raw operand)
+//   1     d g1 = dY8 . Wd2                 128              2                      TMEM
+//   2     d g0 = dY7 . Wd1                 128              2                      TMEM
+//   3     d h5 = dY6 . M1 + d sigma . m2   128 + 128        1 (smem, k=3) + 2      SMEM atom + TMEM
+//   4..8  d h4..h0 = dY . W5, W4, W3[:,171:], W2, W1   128 + 128   4               TMEM
+// The epilogue of step s multiplies by the ReLU mask of forward layer (8 - s) and yields dY(8 - s).
+constexpr int kBwdSteps = 9;
+NFB_HD constexpr StepInfo bwd_step_info(int s) {
+  return s == 0   ? StepInfo{128, 0, 1, 1, 0, 0}
+         : s <= 2 ? StepInfo{128, 0, 2, 0, 0, 0}
+         : s == 3 ? StepInfo{128, 128, 3, 1, 0, 0}
+                  : StepInfo{128, 128, 4, 0, 0, 0};
+}
+NFB_HD constexpr int bwd_step_bytes(int s) { return (bwd_step_info(s).nh0 + bwd_step_info(s).nh1) * bwd_step_info(s).k_atoms * 128; }
+NFB_HD constexpr int bwd_step_offset(int s) {
+  int off = 0;
+  for (int i = 0; i < s; ++i) off += bwd_step_bytes(i);
+  return off;
+}
+constexpr int kBwdStreamBytes = bwd_step_offset(kBwdSteps);  // 835584
+
+// Weight-gradient accumulators of one network (FP32, float offsets), in the kernel's folded parametrisation.
+constexpr int kAcc0 = 0;                       // [256][64]   d W0[:, PE lanes]
+constexpr int kAcc1 = kAcc0 + 256 * 64;        // [256][256]
+constexpr int kAcc2 = kAcc1 + 65536;
+constexpr int kAcc3a = kAcc2 + 65536;          // [256][64]   d W3[:, PE lanes]
+constexpr int kAcc3b = kAcc3a + 256 * 64;      // [256][256]  d W3[:, 171:427]
+constexpr int kAcc4 = kAcc3b + 65536;
+constexpr int kAcc5 = kAcc4 + 65536;
+constexpr int kAcc6 = kAcc5 + 65536;           // [128][256]  d M1 (layers_dir.0[:, :256] . fc_feat)
+constexpr int kAcc6d = kAcc6 + 128 * 256;      // [128][32]   d layers_dir.0[:, 256:280]
+constexpr int kAccSig = kAcc6d + 128 * 32;     // [256][16]   column 3 = d m2 (fc_alpha . fc_feat)
+constexpr int kAcc7 = kAccSig + 256 * 16;      // [128][128]
+constexpr int kAcc8 = kAcc7 + 128 * 128;
+constexpr int kAcc9 = kAcc8 + 128 * 128;       // [128][16]   transposed: [k][n], n < 3 = d fc_rgb.weight[n][k]
+constexpr int kAccB = kAcc9 + 128 * 16;        // biases: b0..b5 [256] each, b6..b8 [128] each, then [4] = (d b_rgb[3], d b_sigma)
+constexpr int kAccBRaw = kAccB + 6 * 256 + 3 * 128;
+constexpr int kAccFloats = kAccBRaw + 4;
+NFB_HD constexpr int acc_bias_off(int layer) { return kAccB + (layer < 6 ? layer * 256 : 1536 + (layer - 6) * 128); }
+
 // Algorithmic cost used for the roofline: 550,016 MAC per MLP evaluation.
 constexpr long long kAlgoFlopPerEval = 1100032LL;
 // MACs the kernel actually issues per evaluation after the folds above.

@@ -30,6 +30,7 @@
 #include "nfb_internal.h"
 #include "nfb_layout.h"
 #include "nfb_ptx.cuh"
+#include "nfb_save.cuh"
 
 namespace nfb {
 
@@ -176,9 +177,9 @@ struct PhaseTimer {
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue math of one 32-column accumulator chunk: x = acc + bias (+ extra); ReLU; FP16 hi (and lo).
-template <bool EXACT>
+template <bool EXACT, bool SAVE>
 __device__ __forceinline__ void epi_math(const uint32_t (&v)[32], uint32_t bias, uint32_t extra,
-                                         float* __restrict__ dump, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+                                         float* __restrict__ dump, uint32_t (&hi)[16], uint32_t (&lo)[16], uint32_t& mask) {
   float x[32];  // bias / extra are shared-memory byte addresses (extra == 0: none)
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -197,6 +198,11 @@ __device__ __forceinline__ void epi_math(const uint32_t (&v)[32], uint32_t bias,
 #pragma unroll
     for (int j = 0; j < 32; ++j) dump[j] = fmaxf(x[j], 0.f);
   }
+  if constexpr (SAVE) {  // ReLU mask of these 32 outputs (bit j = output j is active), for the backward chain
+    mask = 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mask |= (x[j] > 0.f ? 1u : 0u) << j;
+  }
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
     if constexpr (EXACT) {
@@ -213,14 +219,27 @@ __device__ __forceinline__ void epi_math(const uint32_t (&v)[32], uint32_t bias,
 // Epilogue of one 64-column accumulator slice (this thread's share of one N-half): both TMEM loads in flight,
 // two independent bias/ReLU/convert chains, then the FP16 result overwrites the slice in place — hi in columns
 // [0,32), lo (exact mode) in [32,64).  All reads complete (wait::ld) before the first store.
-template <bool EXACT>
-__device__ __forceinline__ void epi_half(uint32_t t_slice, uint32_t bias, uint32_t extra, float* __restrict__ dump) {
+//
+// SAVE (training forward): the FP16 activations are also written to the tile record as a transposed image
+// (`img_row` = image + img_row_base of this thread's sample row `r`, features [k0, k0+64)) and the ReLU mask words
+// to `mask_out[0..1]`.
+template <bool EXACT, bool SAVE>
+__device__ __forceinline__ void epi_half(uint32_t t_slice, uint32_t bias, uint32_t extra, float* __restrict__ dump,
+                                         uint8_t* __restrict__ img_row, int r, int k0, uint32_t* __restrict__ mask_out) {
   uint32_t va[32], vb[32], ha[16], hb[16], la[16], lb[16];
+  uint32_t ma = 0u, mb = 0u;
   tmem_ld32(t_slice, va);
   tmem_ld32(t_slice + 32, vb);
   tmem_wait_ld();
-  epi_math<EXACT>(va, bias, extra, dump, ha, la);
-  epi_math<EXACT>(vb, bias + 128, extra ? extra + 128 : 0u, dump ? dump + 32 : nullptr, hb, lb);
+  epi_math<EXACT, SAVE>(va, bias, extra, dump, ha, la, ma);
+  epi_math<EXACT, SAVE>(vb, bias + 128, extra ? extra + 128 : 0u, dump ? dump + 32 : nullptr, hb, lb, mb);
+  if constexpr (SAVE) {
+    if (img_row) {
+      store_t32(img_row, r, k0, ha);
+      store_t32(img_row, r, k0 + 32, hb);
+      *reinterpret_cast<uint2*>(mask_out) = make_uint2(ma, mb);
+    }
+  }
   tmem_st16(t_slice, ha);
   tmem_st16(t_slice + 16, hb);
   if constexpr (EXACT) {
@@ -296,7 +315,7 @@ __device__ __forceinline__ float composite_ray(const float4* __restrict__ pre, c
 __device__ __forceinline__ uint32_t cta_rank_early() { return cluster_ctarank(); }
 
 // ------------------------------------------------------------------------------------------------
-template <bool EXACT>
+template <bool EXACT, bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
   // Use the dynamic shared array directly (no integer round trip) so the compiler keeps the shared address
   // space and emits LDS/STS instead of generic loads; the swizzled operands need 1024-byte alignment.
@@ -498,6 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           rp.dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
           if (has_bg) { rp.bg[0] = p.bg[3 * g]; rp.bg[1] = p.bg[3 * g + 1]; rp.bg[2] = p.bg[3 * g + 2]; }
           rp.dz = p.dir_z ? p.dir_z[g] : d2;
+          if constexpr (SAVE) p.save_dnorm[g] = rp.dnorm;
         } else {
           for (int k = 0; k < 3; ++k) { rp.o[k] = 0.f; rp.d[k] = 0.f; rp.bg[k] = 0.f; }
           rp.dnorm = 0.f;
@@ -612,6 +632,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 #pragma unroll
             for (int k = 0; k < 32; ++k) p.dbg_act[row * 256 + ch * 32 + k] = f[k];
           }
+          if constexpr (SAVE) {  // FP16 encoding of this tile as a transposed image (input of layers_xyz.0 / .3 in dW)
+            if (unit < p.n_units) {
+              uint8_t* rec = p.save_rec + (size_t)(unit * tiles_per_unit + (pass ? p.tiles_c : 0) + t) * kRecBytes;
+              uint32_t hh[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) hh[e] = pack_f16x2(f[2 * e], f[2 * e + 1]);
+              store_t32(rec + kRecPE + img_row_base(64, row), row, 32 * ch, hh);
+            }
+          }
           fence_proxy_async_smem();  // make the generic-proxy PE stores visible to the tensor core
         };
 
@@ -625,6 +654,31 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           const int r = live ? prow / S : 0;
           const int i = live ? prow - r * S : 0;
           const RayP& rp = rayp[r];
+          uint8_t* rec = nullptr;  // this tile's training record (SAVE mode, real units only)
+          if constexpr (SAVE) {
+            if (unit < p.n_units) {
+              rec = p.save_rec + (size_t)(unit * tiles_per_unit + (pass ? p.tiles_c : 0) + t) * kRecBytes;
+              uint32_t hh[16];  // direction encoding of this row's ray: features [16*ch, 16*ch+16) -> two 8-feature halves
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int k = 16 * ch + 2 * e;
+                const float a = (live && rp.valid && k < kDimDir) ? rp.ped[k] : 0.f;
+                const float b = (live && rp.valid && k + 1 < kDimDir) ? rp.ped[k + 1] : 0.f;
+                hh[e] = pack_f16x2(a, b);
+              }
+#pragma unroll
+              for (int e = 8; e < 16; ++e) hh[e] = 0u;
+              // store_t32 writes 32 features; only 16 belong to this thread, so store the first 8 words by hand
+              uint8_t* img = rec + kRecPEd + img_row_base(32, row);
+              const uint32_t cr = (uint32_t)((row & 63) >> 3);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int ka = 16 * ch + 2 * e, kb = ka + 1;
+                *reinterpret_cast<uint16_t*>(img + ka * 128 + ((cr ^ (uint32_t)(ka & 7)) << 4)) = (uint16_t)(hh[e] & 0xFFFFu);
+                *reinterpret_cast<uint16_t*>(img + kb * 128 + ((cr ^ (uint32_t)(kb & 7)) << 4)) = (uint16_t)(hh[e] >> 16);
+              }
+            }
+          }
           __syncwarp();
           if (lane == 0) {  // PE buffer of tile t is in place (fenced inside prologue): both gates of step 0
             mbar_arrive(bar_aready);
@@ -656,7 +710,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               const int c0 = 64 * ch;
               if (s == 6 && t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias written by all threads
               const uint32_t extra = (s == 6) ? smem_u32(dirbias + r * 128 + c0) : 0u;
-              epi_half<EXACT>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), extra, dump ? dump + c0 : nullptr);
+              uint8_t* img = rec ? rec + rec_x_off(s) + img_row_base(rec_width(s), row) : nullptr;
+              uint32_t* mk = rec ? reinterpret_cast<uint32_t*>(rec + kRecMask) + (s * 128 + row) * 8 + (c0 >> 5) : nullptr;
+              epi_half<EXACT, SAVE>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), extra, dump ? dump + c0 : nullptr, img, row, c0, mk);
             } else if (ch == 0) {
               // fc_rgb output.  Prepare what compositing needs per sample: colour and sigma
               // (volume_rendering_utils.py:29-33, 41-53); the exp(-sigma*delta) needs the neighbour depth and
@@ -674,6 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                 float sig = sigma_raw;
                 if (p.noise_std > 0.f && rp.valid)
                   sig = __fadd_rn(sig, __fmul_rn((pass ? p.noise_f : p.noise_c)[(size_t)rp.gidx * S + i], p.noise_std));
+                const float sig_in = sig;  // what the ReLU sees (volume_rendering_utils.py:52)
                 sig = fmaxf(sig, 0.f);
                 float4 pre;
                 if (i == S - 1) {
@@ -687,6 +744,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                 }
                 pre.w = sig;
                 carry_raw[prow] = pre;
+                if constexpr (SAVE) {  // what the compositing backward needs: colour (or bg) and the ReLU input
+                  if (rp.valid) reinterpret_cast<float4*>(pass ? p.save_raw_f : p.save_raw_c)[(size_t)rp.gidx * S + i] = make_float4(pre.x, pre.y, pre.z, sig_in);
+                }
               }
             }
             if (s < kNumSteps - 1) {
@@ -700,7 +760,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             tm.lap(30 + (s < 8 ? s : 7));
             if (s <= 5) {
               const int c0 = 128 + 64 * ch;
-              epi_half<EXACT>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), 0u, dump ? dump + c0 : nullptr);
+              uint8_t* img = rec ? rec + rec_x_off(s) + img_row_base(rec_width(s), row) : nullptr;
+              uint32_t* mk = rec ? reinterpret_cast<uint32_t*>(rec + kRecMask) + (s * 128 + row) * 8 + (c0 >> 5) : nullptr;
+              epi_half<EXACT, SAVE>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), 0u, dump ? dump + c0 : nullptr, img, row, c0, mk);
             } else if (s == 6 && ch == 0) {  // sigma = first column of half 1 of the folded layers_dir.0 | fc_alpha step
               uint32_t v[4];
               tmem_ld4(t_acc + 128, v);
@@ -861,9 +923,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 }
 
 cudaError_t render_kernel_setup() {
-  cudaError_t e = cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(render_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  e = cudaFuncSetAttribute(render_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(render_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(render_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 }
 
 cudaError_t launch_render(const RenderParams& p, int precision, int num_sms, cudaStream_t st, long long* launches) {
@@ -883,7 +949,10 @@ cudaError_t launch_render(const RenderParams& p, int precision, int num_sms, cud
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = (precision == 1) ? cudaLaunchKernelEx(&cfg, render_kernel<true>, p) : cudaLaunchKernelEx(&cfg, render_kernel<false>, p);
+  const bool save = p.save_rec != nullptr;  // training forward: also writes the per-tile activation records
+  cudaError_t e;
+  if (precision == 1) e = save ? cudaLaunchKernelEx(&cfg, render_kernel<true, true>, p) : cudaLaunchKernelEx(&cfg, render_kernel<true, false>, p);
+  else e = save ? cudaLaunchKernelEx(&cfg, render_kernel<false, true>, p) : cudaLaunchKernelEx(&cfg, render_kernel<false, false>, p);
   ++*launches;
   return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -11,7 +11,8 @@ NFB_NET_COARSE, NFB_NET_FINE = 0, 1
 NFB_PREC_FAST, NFB_PREC_EXACT = 0, 1
 
 EXPORTS = ["nfb_version", "nfb_strerror", "nfb_last_cuda_error", "nfb_create", "nfb_destroy", "nfb_load_weights",
-           "nfb_set_frame", "nfb_render_forward", "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace"]
+           "nfb_set_frame", "nfb_render_forward", "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace",
+           "nfb_render_forward_train", "nfb_render_backward", "nfb_train_debug"]
 
 
 class NfbModelDims(C.Structure):
@@ -45,6 +46,18 @@ class NfbDebug(C.Structure):
                 ("act_dump", C.c_void_p), ("act_step", C.c_int32), ("prof", C.c_void_p)]
 
 
+class NfbOutGrads(C.Structure):
+    _fields_ = [("rgb_coarse", C.c_void_p), ("disp_coarse", C.c_void_p), ("acc_coarse", C.c_void_p),
+                ("rgb_fine", C.c_void_p), ("disp_fine", C.c_void_p), ("acc_fine", C.c_void_p), ("w_last", C.c_void_p)]
+
+
+class NfbTrainDebug(C.Structure):
+    _fields_ = [("records", C.c_void_p), ("n_tiles", C.c_longlong), ("record_bytes", C.c_int32), ("d_raw", C.c_void_p),
+                ("acc_coarse", C.c_void_p), ("acc_fine", C.c_void_p), ("acc_floats", C.c_int32), ("scale", C.c_void_p),
+                ("z_coarse", C.c_void_p), ("raw_coarse", C.c_void_p), ("z_fine", C.c_void_p), ("raw_fine", C.c_void_p),
+                ("tiles_coarse", C.c_int32), ("tiles_fine", C.c_int32), ("rays_per_unit", C.c_int32)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} not found: build it with `python 4d-facial-avatars_b200/build.py` "
@@ -63,10 +76,16 @@ def _load():
     lib.nfb_render_frame_host.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(NfbSampling), C.c_void_p, C.c_void_p]
+    lib.nfb_render_forward_train.argtypes = [C.c_void_p, C.POINTER(NfbRays), C.POINTER(NfbSampling), C.POINTER(NfbNoise),
+                                             C.POINTER(NfbOutputs), C.c_void_p]
+    lib.nfb_render_backward.argtypes = [C.c_void_p, C.POINTER(NfbOutGrads), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
+    lib.nfb_train_debug.argtypes = [C.c_void_p, C.POINTER(NfbTrainDebug)]
     lib.nfb_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     lib.nfb_host_linspace.argtypes = [C.POINTER(C.c_float), C.c_int]
     for fn in ("nfb_create", "nfb_destroy", "nfb_load_weights", "nfb_set_frame", "nfb_render_forward",
-               "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace"):
+               "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace", "nfb_render_forward_train",
+               "nfb_render_backward", "nfb_train_debug"):
         getattr(lib, fn).restype = C.c_int
     return lib
 

@@ -57,6 +57,7 @@ class Renderer:
         self._lin = {}
         self._versions = [None, None]
         self._keep = [None, None]  # contiguous FP32 copies handed to the pack kernels
+        self.train_token = 0       # bumped by every training forward: the handle keeps ONE saved state
         weakref.finalize(self, capi.lib.nfb_destroy, h)
 
     @staticmethod
@@ -100,9 +101,10 @@ class Renderer:
         return n.value
 
     def render(self, ro, rd, near, far, num_coarse, num_fine, perturb=False, noise_std=0.0, white_bkgd=False,
-               background=None, dir_z=None, noise=None, precision=None, debug=False, act_step=None):
+               background=None, dir_z=None, noise=None, precision=None, debug=False, act_step=None, train=False):
         """ro, rd: [N,3] CUDA FP32.  noise: dict with t_rand, n_c, u, n_f (any may be None).  Returns a dict
-        with the seven outputs (+ per-sample dumps when debug)."""
+        with the seven outputs (+ per-sample dumps when debug).  train=True: nfb_render_forward_train (the handle keeps
+        the state `backward` consumes)."""
         dev = self.device
         ro, rd = _f32c(ro, dev), _f32c(rd, dev)
         n = ro.shape[0]
@@ -154,11 +156,50 @@ class Renderer:
             if act_step is not None:
                 out["act"] = torch.zeros((128, 256), device=dev)
                 dbg.act_dump, dbg.act_step = out["act"].data_ptr(), int(act_step)
-        capi.check(capi.lib.nfb_render_forward(self._h, C.byref(rays), C.byref(sm), C.byref(nz) if noise else None,
-                                               C.byref(o), C.byref(dbg) if dbg is not None else None, _stream()),
-                   "render_forward")
+        if train:
+            self.train_token += 1
+            capi.check(capi.lib.nfb_render_forward_train(self._h, C.byref(rays), C.byref(sm), C.byref(nz) if noise else None,
+                                                         C.byref(o), _stream()), "render_forward_train")
+        else:
+            capi.check(capi.lib.nfb_render_forward(self._h, C.byref(rays), C.byref(sm), C.byref(nz) if noise else None,
+                                                   C.byref(o), C.byref(dbg) if dbg is not None else None, _stream()),
+                       "render_forward")
         out["_keep"] = keep  # inputs must outlive the asynchronous launch
         return out
+
+    def backward(self, out_grads, params_c, params_f, want_latent=True):
+        """nfb_render_backward for the last training forward.  out_grads: 7 CUDA tensors or None (rgb_c, disp_c, acc_c,
+        rgb_f, disp_f, acc_f, w_last); params_*: the 26 FP32 parameter tensors in PARAM_ORDER (params_f None without a
+        fine network).  Returns (grads_c, grads_f, grad_latent) — lists aligned with PARAM_ORDER, None for layers_dir.3.*."""
+        dev = self.device
+        keep = []
+        og = capi.NfbOutGrads()
+        for field, g in zip(("rgb_coarse", "disp_coarse", "acc_coarse", "rgb_fine", "disp_fine", "acc_fine", "w_last"), out_grads):
+            if g is not None:
+                g = _f32c(g, dev)
+                keep.append(g)
+                setattr(og, field, g.data_ptr())
+
+        def pack(params):
+            if params is None:
+                return None, None, None
+            ps = [_f32c(t, dev) for t in params]
+            gs = [None if PARAM_ORDER[i].startswith("layers_dir.3") else torch.empty_like(ps[i]) for i in range(26)]
+            keep.extend(ps)
+            return ((C.c_void_p * 26)(*[t.data_ptr() for t in ps]),
+                    (C.c_void_p * 26)(*[(g.data_ptr() if g is not None else None) for g in gs]), gs)
+
+        pc, gc, grads_c = pack(params_c)
+        pf, gf, grads_f = pack(params_f)
+        glat = torch.empty(32, device=dev, dtype=torch.float32) if want_latent else None
+        capi.check(capi.lib.nfb_render_backward(self._h, C.byref(og), pc, pf, gc, gf, _ptr(glat), _stream()), "render_backward")
+        self._bwd_keep = keep
+        return grads_c, grads_f, glat
+
+    def train_debug(self):
+        d = capi.NfbTrainDebug()
+        capi.check(capi.lib.nfb_train_debug(self._h, C.byref(d)), "train_debug")
+        return d
 
     def render_camera(self, pose, intrinsics, height, width, row_begin, rows, near, far, num_coarse, num_fine,
                       background=None, out=None, precision=None, white_bkgd=False, prof=None):

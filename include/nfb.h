@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NFB_VERSION 100
+#define NFB_VERSION 110
 
 typedef struct NfbHandle NfbHandle;
 
@@ -156,6 +156,50 @@ int nfb_set_frame(NfbHandle* h, const float* expression, const float* latent, vo
 int nfb_render_forward(NfbHandle* h, const NfbRays* rays, const NfbSampling* sampling,
                        const NfbNoise* noise /* nullable */, const NfbOutputs* out,
                        const NfbDebug* dbg /* nullable */, void* stream);
+
+/* ---- Training (replaces torch.autograd over the unfused graph, train_transformed_rays.py:389) ----
+ * nfb_render_forward_train is nfb_render_forward that additionally keeps, in buffers owned by the handle, what the
+ * backward needs: per-sample depths, colours and ReLU inputs of both passes, and per 128-row tile the FP16 activations
+ * of every layer (about 1 MiB per tile; 2048 rays at 64+64 samples = 3 GiB).  The next nfb_render_backward on the same
+ * handle consumes that state; weights must not be re-loaded in between. */
+int nfb_render_forward_train(NfbHandle* h, const NfbRays* rays, const NfbSampling* sampling,
+                             const NfbNoise* noise /* nullable */, const NfbOutputs* out, void* stream);
+
+/* dL/d(outputs) of the 7-tuple; any member may be NULL (= zero).  All device pointers, shapes as NfbOutputs. */
+typedef struct {
+  const float* rgb_coarse;
+  const float* disp_coarse;
+  const float* acc_coarse;
+  const float* rgb_fine;
+  const float* disp_fine;
+  const float* acc_fine;
+  const float* w_last;
+} NfbOutGrads;
+
+/* Backward of the last nfb_render_forward_train: compositing backward -> tcgen05 dX chain -> tcgen05 weight-gradient GEMMs
+ * -> gradients in the reference's parameter layout.  `params_*` are the 26 FP32 parameter pointers given to
+ * nfb_load_weights; `grads_*` receive dL/dparam with the same shapes (entries 22, 23 = layers_dir.3.*, unused by the
+ * forward, models.py:257: may be NULL and are never written).  `grad_latent` [32] receives dL/d latent_code (NULL: skipped);
+ * the sample depths carry no gradient (z_samples.detach(), train_utils.py:124).  Gradients are OVERWRITTEN, not accumulated.
+ * params_fine / grads_fine may be NULL when the forward had num_fine == 0. */
+int nfb_render_backward(NfbHandle* h, const NfbOutGrads* out_grads, const float* const params_coarse[26],
+                        const float* const params_fine[26], float* const grads_coarse[26], float* const grads_fine[26],
+                        float* grad_latent, void* stream);
+
+/* Test hook: device pointers of the training state (valid until the next forward_train on the handle). */
+typedef struct {
+  const uint8_t* records;      /* n_tiles records of record_bytes (layout: nfb_layout.h kRec*) */
+  long long n_tiles;
+  int32_t record_bytes;
+  const float* d_raw;          /* [n_tiles][128][4] dL/d(rgb_raw, sigma_raw), unscaled */
+  const float* acc_coarse;     /* acc_floats accumulators in the kernel's folded parametrisation (kAcc*) */
+  const float* acc_fine;
+  int32_t acc_floats;
+  const float* scale;          /* [0] loss scale, [1] its inverse */
+  const float *z_coarse, *raw_coarse, *z_fine, *raw_fine;
+  int32_t tiles_coarse, tiles_fine, rays_per_unit;
+} NfbTrainDebug;
+int nfb_train_debug(NfbHandle* h, NfbTrainDebug* out);
 
 /* End-to-end convenience for callers with HOST buffers (bench.py's e2e leg, C/C++ users): copies
  * expression/latent/background to the device, renders image rows [row_begin,row_begin+rows) of a
