@@ -36,11 +36,19 @@ __global__ void fold_feat_kernel(const float* __restrict__ Wf, const float* __re
   }
 }
 
-// One thread per 16-byte chunk (8 consecutive K) of one weight row of unit `u` of step `s`.
-__global__ void pack_step_kernel(const float* __restrict__ src, int ld, int n_valid, int s, uint8_t* __restrict__ dst_x1,
-                                 uint8_t* __restrict__ dst_x3) {
+// One thread per 16-byte chunk (8 consecutive K) of one weight row of unit `u` (blockIdx.y) of step `s` (blockIdx.z).
+struct PackArgs {
+  const float* src[kNumSteps];  // step -> source matrix (row-major [out, in])
+  int ld[kNumSteps];            // leading dimension
+  int n_valid[kNumSteps];       // valid output rows
+};
+__global__ void pack_step_kernel(PackArgs a, uint8_t* __restrict__ dst_x1, uint8_t* __restrict__ dst_x3) {
+  const int s = blockIdx.z;
   const StepInfo si = step_info(s);
   const int u = blockIdx.y;
+  if (u >= num_units(s)) return;
+  const float* __restrict__ src = a.src[s];
+  const int ld = a.ld[s], n_valid = a.n_valid[s];
   const UnitInfo ui = unit_info(s, u);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ui.rows * 8) return;
@@ -132,14 +140,18 @@ cudaError_t launch_load_weights(NetBuffers& nb, const float* const params[26], c
   for (int i = 0; i < 26; ++i) g.p[i] = params[i];
   gather_kernel<<<(256 * kDimCond + 255) / 256, 256, 0, st>>>(g, nb.b6, nb.bias_static, nb.w0c, nb.w3c, nb.wd0b_t);
   ++*launches;
-  // step -> (source matrix, leading dimension, valid rows)
+  // step -> (source matrix, leading dimension, valid rows); one launch packs every unit of every step
+  PackArgs a;
   const float* src[kNumSteps] = {params[0], params[2], params[4], params[6], params[8], params[10], nb.w6, params[18], params[20], params[24]};
   const int ld[kNumSteps] = {171, 256, 256, 427, 256, 256, 256, 128, 128, 128};
   const int nv[kNumSteps] = {256, 256, 256, 256, 256, 256, 129, 128, 128, 3};
+  int max_units = 0;
   for (int s = 0; s < kNumSteps; ++s) {
-    pack_step_kernel<<<dim3(8, num_units(s)), 256, 0, st>>>(src[s], ld[s], nv[s], s, nb.stream_x1, nb.stream_x3);
-    ++*launches;
+    a.src[s] = src[s]; a.ld[s] = ld[s]; a.n_valid[s] = nv[s];
+    if (num_units(s) > max_units) max_units = num_units(s);
   }
+  pack_step_kernel<<<dim3(8, max_units, kNumSteps), 256, 0, st>>>(a, nb.stream_x1, nb.stream_x3);
+  ++*launches;
   return cudaGetLastError();
 }
 

@@ -220,26 +220,17 @@ __device__ __forceinline__ void epi_math(const uint32_t (&v)[32], uint32_t bias,
 // two independent bias/ReLU/convert chains, then the FP16 result overwrites the slice in place — hi in columns
 // [0,32), lo (exact mode) in [32,64).  All reads complete (wait::ld) before the first store.
 //
-// SAVE (training forward): the FP16 activations are also written to the tile record as a transposed image
-// (`img_row` = image + img_row_base of this thread's sample row `r`, features [k0, k0+64)) and the ReLU mask words
-// to `mask_out[0..1]`.
+// SAVE (training forward): the FP16 values and the ReLU mask words are handed back so that the caller can write them to
+// the tile record AFTER it has signalled the gate (the stores then overlap the next step's tensor-core work).
 template <bool EXACT, bool SAVE>
 __device__ __forceinline__ void epi_half(uint32_t t_slice, uint32_t bias, uint32_t extra, float* __restrict__ dump,
-                                         uint8_t* __restrict__ img_row, int r, int k0, uint32_t* __restrict__ mask_out) {
-  uint32_t va[32], vb[32], ha[16], hb[16], la[16], lb[16];
-  uint32_t ma = 0u, mb = 0u;
+                                         uint32_t (&ha)[16], uint32_t (&hb)[16], uint32_t& ma, uint32_t& mb) {
+  uint32_t va[32], vb[32], la[16], lb[16];
   tmem_ld32(t_slice, va);
   tmem_ld32(t_slice + 32, vb);
   tmem_wait_ld();
   epi_math<EXACT, SAVE>(va, bias, extra, dump, ha, la, ma);
   epi_math<EXACT, SAVE>(vb, bias + 128, extra ? extra + 128 : 0u, dump ? dump + 32 : nullptr, hb, lb, mb);
-  if constexpr (SAVE) {
-    if (img_row) {
-      store_t32(img_row, r, k0, ha);
-      store_t32(img_row, r, k0 + 32, hb);
-      *reinterpret_cast<uint2*>(mask_out) = make_uint2(ma, mb);
-    }
-  }
   tmem_st16(t_slice, ha);
   tmem_st16(t_slice + 16, hb);
   if constexpr (EXACT) {
@@ -706,13 +697,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             ph_acc0 ^= 1;
             tc_fence_after_sync();
             tm.lap(10 + s);
+            uint32_t ha[16], hb[16], ma = 0u, mb = 0u;  // FP16 activations / ReLU mask of this thread's slice (SAVE)
             if (s <= 8) {  // ReLU layers: this thread converts output columns [64*ch, 64*ch+64) of the half in place
               const int c0 = 64 * ch;
               if (s == 6 && t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias written by all threads
               const uint32_t extra = (s == 6) ? smem_u32(dirbias + r * 128 + c0) : 0u;
-              uint8_t* img = rec ? rec + rec_x_off(s) + img_row_base(rec_width(s), row) : nullptr;
-              uint32_t* mk = rec ? reinterpret_cast<uint32_t*>(rec + kRecMask) + (s * 128 + row) * 8 + (c0 >> 5) : nullptr;
-              epi_half<EXACT, SAVE>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), extra, dump ? dump + c0 : nullptr, img, row, c0, mk);
+              epi_half<EXACT, SAVE>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), extra, dump ? dump + c0 : nullptr, ha, hb, ma, mb);
             } else if (ch == 0) {
               // fc_rgb output.  Prepare what compositing needs per sample: colour and sigma
               // (volume_rendering_utils.py:29-33, 41-53); the exp(-sigma*delta) needs the neighbour depth and
@@ -755,14 +745,21 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_aready);
             }
+            if constexpr (SAVE) {  // after the gate: the record stores overlap the next step's MMAs
+              if (rec && s <= 8) {
+                const int c0 = 64 * ch;
+                uint8_t* img = rec + rec_x_off(s) + img_row_base(rec_width(s), row);
+                store_t32(img, row, c0, ha);
+                store_t32(img, row, c0 + 32, hb);
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(rec + kRecMask) + (s * 128 + row) * 8 + (c0 >> 5)) = make_uint2(ma, mb);
+              }
+            }
             tm.lap(20 + s);
             // ---------------- half 1 (same accumulator, columns [128,256))
             tm.lap(30 + (s < 8 ? s : 7));
             if (s <= 5) {
               const int c0 = 128 + 64 * ch;
-              uint8_t* img = rec ? rec + rec_x_off(s) + img_row_base(rec_width(s), row) : nullptr;
-              uint32_t* mk = rec ? reinterpret_cast<uint32_t*>(rec + kRecMask) + (s * 128 + row) * 8 + (c0 >> 5) : nullptr;
-              epi_half<EXACT, SAVE>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), 0u, dump ? dump + c0 : nullptr, img, row, c0, mk);
+              epi_half<EXACT, SAVE>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), 0u, dump ? dump + c0 : nullptr, ha, hb, ma, mb);
             } else if (s == 6 && ch == 0) {  // sigma = first column of half 1 of the folded layers_dir.0 | fc_alpha step
               uint32_t v[4];
               tmem_ld4(t_acc + 128, v);
@@ -774,6 +771,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               tc_fence_before_sync();
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_aready + 8);
+            }
+            if constexpr (SAVE) {
+              if (rec && s <= 5) {
+                const int c0 = 128 + 64 * ch;
+                uint8_t* img = rec + rec_x_off(s) + img_row_base(256, row);
+                store_t32(img, row, c0, ha);
+                store_t32(img, row, c0 + 32, hb);
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(rec + kRecMask) + (s * 128 + row) * 8 + (c0 >> 5)) = make_uint2(ma, mb);
+              }
             }
             tm.lap(48 + s);
             if (s == 3 && t + 1 < n_tiles) {  // PE buffer is free: encode the next tile under steps 4..9

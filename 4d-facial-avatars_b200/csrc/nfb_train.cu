@@ -135,10 +135,12 @@ __host__ __device__ constexpr BwdUnit bwd_unit_info(int s, int u) {
 __host__ __device__ constexpr int bwd_unit_offset(int s, int u) { return bwd_step_offset(s) + u * (bwd_step_info(s).nh0 + bwd_step_info(s).nh1) * 128; }
 
 struct PackBwdArgs { const float* p[26]; const float* w6; };
-// One thread per 16-byte chunk (8 consecutive k) of one row n of unit (s, u).
-__global__ void pack_bwd_kernel(PackBwdArgs a, int s, uint8_t* __restrict__ dst) {
+// One thread per 16-byte chunk (8 consecutive k) of one row n of unit (s = blockIdx.z, u = blockIdx.y).
+__global__ void pack_bwd_kernel(PackBwdArgs a, uint8_t* __restrict__ dst) {
+  const int s = blockIdx.z;
   const StepInfo si = bwd_step_info(s);
   const int u = blockIdx.y;
+  if (u >= si.k_atoms) return;
   const int rows = si.nh0 + si.nh1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * 8) return;
@@ -172,10 +174,8 @@ cudaError_t launch_pack_bwd(NetBuffers& nb, const float* const params[26], cudaS
   PackBwdArgs a;
   for (int i = 0; i < 26; ++i) a.p[i] = params[i];
   a.w6 = nb.w6;
-  for (int s = 0; s < kBwdSteps; ++s) {
-    pack_bwd_kernel<<<dim3(8, bwd_step_info(s).k_atoms), 256, 0, st>>>(a, s, nb.stream_bwd);
-    ++*launches;
-  }
+  pack_bwd_kernel<<<dim3(8, 4, kBwdSteps), 256, 0, st>>>(a, nb.stream_bwd);
+  ++*launches;
   return cudaGetLastError();
 }
 
@@ -480,39 +480,46 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
 namespace dw {
 
 constexpr int kThreads = 192;  // warp 0 producer, warp 1 MMA issuer, warps 2..5 epilogue (one per TMEM lane quadrant)
-constexpr int kStages = 2;
-constexpr int kStageBytes = 32768 + 65536;       // A: 2 r-atoms x [128 rows x 128 B]; B: 2 r-atoms x [<=256 rows x 128 B]
+constexpr int kStages = 4;
+constexpr int kStageBytes = 16384 + 32768;       // one r-atom (64 sample rows): A [128 features x 128 B], B [<=256 features x 128 B]
 constexpr int kOffOnes = kStages * kStageBytes;  // [16 rows x 64 r]: row 0 = 1.0 (bias = column sums of dY)
 constexpr int kOffBars = kOffOnes + 2048;
-constexpr int kOffTmemPtr = kOffBars + 8 * 8;
+constexpr int kOffTmemPtr = kOffBars + (2 * kStages + 2) * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 constexpr uint32_t kBiasCol = 256;
 
 struct Job {
-  int a_off, a_rows, a_half;  // A image (M side): record offset, features in the image, which 128-row half
+  int a_off, a_rows, a_half;  // A image (M side): record offset, features in the image, which 128-feature half
   int b_off, b_rows;          // B image (N side): record offset, features (= MMA N)
   int bias_layer;             // >= 0: also accumulate column sums of A into the bias of this layer
   int out_off, out_ld, out_row0;
 };
+// Jobs are dealt to kGroups groups of CTAs of roughly equal tensor-core work; within a group every CTA runs the group's
+// jobs over its own share of the tiles (fewer accumulator drains and atomics than every CTA running every job).
 constexpr int kNumJobs = 21;
-struct JobTable { Job j[kNumJobs]; };
+constexpr int kGroups = 4;
+struct JobTable { Job j[kNumJobs]; int group_begin[kGroups + 1]; };
 constexpr JobTable make_jobs() {
   JobTable t{};
   int i = 0;
-  // layers_xyz.0: dY0 x PE
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(0), 256, h, kRecPE, 64, 0, kAcc0, 64, 128 * h};
+  t.group_begin[0] = i;
   for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(1), 256, h, rec_x_off(0), 256, 1, kAcc1, 256, 128 * h};
   for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(2), 256, h, rec_x_off(1), 256, 2, kAcc2, 256, 128 * h};
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(3), 256, h, kRecPE, 64, 3, kAcc3a, 64, 128 * h};
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(3), 256, h, rec_x_off(2), 256, -1, kAcc3b, 256, 128 * h};
+  t.group_begin[1] = i;
   for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(4), 256, h, rec_x_off(3), 256, 4, kAcc4, 256, 128 * h};
   for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(5), 256, h, rec_x_off(4), 256, 5, kAcc5, 256, 128 * h};
+  t.group_begin[2] = i;
+  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(3), 256, h, rec_x_off(2), 256, -1, kAcc3b, 256, 128 * h};
   t.j[i++] = Job{rec_dy_off(6), 128, 0, rec_x_off(5), 256, 6, kAcc6, 256, 0};   // d M1
+  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(0), 256, h, kRecPE, 64, 0, kAcc0, 64, 128 * h};  // layers_xyz.0: dY0 x PE
+  t.group_begin[3] = i;
+  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(3), 256, h, kRecPE, 64, 3, kAcc3a, 64, 128 * h};
   t.j[i++] = Job{rec_dy_off(6), 128, 0, kRecPEd, 32, -1, kAcc6d, 32, 0};         // d layers_dir.0[:, 256:280]
   for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_x_off(5), 256, h, kRecDRaw, 16, -1, kAccSig, 16, 128 * h};  // h5^T . d raw
   t.j[i++] = Job{rec_dy_off(7), 128, 0, rec_x_off(6), 128, 7, kAcc7, 128, 0};
   t.j[i++] = Job{rec_dy_off(8), 128, 0, rec_x_off(7), 128, 8, kAcc8, 128, 0};
   t.j[i++] = Job{rec_x_off(8), 128, 0, kRecDRaw, 16, -1, kAcc9, 16, 0};          // g2^T . d raw
+  t.group_begin[4] = i;
   return t;
 }
 __constant__ JobTable c_jobs = make_jobs();
@@ -523,12 +530,15 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
   if ((smem_base & 1023u) != 0u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // this CTA's contiguous range of the network's tiles
+  // this CTA: job group (blockIdx.x % kGroups) x a contiguous share of the network's tiles
+  const int parts = (int)gridDim.x / kGroups;
+  const int group = (int)blockIdx.x % kGroups, part = (int)blockIdx.x / kGroups;
   const int total = p.n_units * p.t_cnt;
-  const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int j0 = (int)blockIdx.x * per;
+  const int per = (total + parts - 1) / parts;
+  const int j0 = part * per;
   const int j1 = min(total, j0 + per);
-  if (j0 >= j1) return;  // uniform for the whole CTA
+  if (part >= parts || j0 >= j1) return;  // uniform for the whole CTA
+  const int job0 = c_jobs.group_begin[group], job1 = c_jobs.group_begin[group + 1];
 
   const uint32_t bar_full = smem_base + kOffBars;      // [kStages]
   const uint32_t bar_empty = bar_full + kStages * 8;   // [kStages]
@@ -565,23 +575,22 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
   if (warp == 0) {
     // ============================== producer ==============================
     uint32_t stage = 0, phase = 0;
-    for (int job = 0; job < kNumJobs; ++job) {
+    for (int job = job0; job < job1; ++job) {
       const Job J = c_jobs.j[job];
       const uint32_t b_bytes = (uint32_t)J.b_rows * 128u;
       for (int j = j0; j < j1; ++j) {
         const uint8_t* rec = tile_rec(j);
-        mbar_wait(bar_empty + stage * 8, phase ^ 1);
-        if (elect_one()) {
-          const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + 32768;
-          mbar_arrive_expect_tx(bar_full + stage * 8, 2 * 16384 + 2 * b_bytes);
-#pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            bulk_g2s(sa + a * 16384, rec + J.a_off + a * J.a_rows * 128 + J.a_half * 16384, 16384, bar_full + stage * 8);
-            bulk_g2s(sb + a * 32768, rec + J.b_off + a * J.b_rows * 128, b_bytes, bar_full + stage * 8);
+        for (int a = 0; a < 2; ++a) {
+          mbar_wait(bar_empty + stage * 8, phase ^ 1);
+          if (elect_one()) {
+            const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + 16384;
+            mbar_arrive_expect_tx(bar_full + stage * 8, 16384 + b_bytes);
+            bulk_g2s(sa, rec + J.a_off + a * J.a_rows * 128 + J.a_half * 16384, 16384, bar_full + stage * 8);
+            bulk_g2s(sb, rec + J.b_off + a * J.b_rows * 128, b_bytes, bar_full + stage * 8);
           }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -589,31 +598,30 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
     uint32_t stage = 0, phase = 0, acc_phase = 0;
     const uint64_t ones_desc = umma_smem_desc_sw128(smem_base + kOffOnes);
     const uint32_t idesc_bias = umma_idesc_f16(128, 16);
-    for (int job = 0; job < kNumJobs; ++job) {
+    for (int job = job0; job < job1; ++job) {
       const Job J = c_jobs.j[job];
       const uint32_t idesc = umma_idesc_f16(128, J.b_rows);
       mbar_wait(bar_accempty, acc_phase ^ 1);  // the epilogue has drained the previous job's accumulator
       tc_fence_after_sync();
       for (int j = j0; j < j1; ++j) {
-        mbar_wait(bar_full + stage * 8, phase);
-        tc_fence_after_sync();
-        const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + 32768;
-        if (elect_one()) {
-#pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const uint64_t ad = umma_smem_desc_sw128(sa + a * 16384), bd = umma_smem_desc_sw128(sb + a * 32768);
+        for (int a = 0; a < 2; ++a) {
+          mbar_wait(bar_full + stage * 8, phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + 16384;
+          if (elect_one()) {
+            const uint64_t ad = umma_smem_desc_sw128(sa), bd = umma_smem_desc_sw128(sb);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t accf = ((j - j0) | a | ks) ? 1u : 0u;
               umma_ss(tmem_base, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accf);
               if (J.bias_layer >= 0) umma_ss(tmem_base + kBiasCol, ad + (uint64_t)(ks * 2), ones_desc + (uint64_t)(ks * 2), idesc_bias, accf);
             }
+            umma_commit(bar_empty + stage * 8);
+            if (j == j1 - 1 && a == 1) umma_commit(bar_accfull);
           }
-          umma_commit(bar_empty + stage * 8);
-          if (j == j1 - 1) umma_commit(bar_accfull);
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       acc_phase ^= 1;
     }
@@ -624,7 +632,7 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const float inv = p.scal[1];
     uint32_t acc_phase = 0;
-    for (int job = 0; job < kNumJobs; ++job) {
+    for (int job = job0; job < job1; ++job) {
       const Job J = c_jobs.j[job];
       mbar_wait(bar_accfull, acc_phase);
       acc_phase ^= 1;
@@ -766,19 +774,25 @@ __global__ void finalize_kernel(const FinArgs a) {
 
 // d latent[j] = sum over networks, n of W0[n][139 + j] db0[n] + W3[n][139 + j] db3[n]
 struct LatArgs { const float* w0[2]; const float* w3[2]; const float* acc[2]; int nets; float* out; };
-__global__ void latent_grad_kernel(const LatArgs a) {
-  const int j = threadIdx.x;
-  if (j >= kDimLatent) return;
+__global__ void latent_grad_kernel(const LatArgs a) {  // one block of 256 threads: thread = (n-chunk of 32 rows, j)
+  __shared__ float part[8][kDimLatent];
+  const int j = threadIdx.x & 31, c = threadIdx.x >> 5;
   float s = 0.f;
   for (int net = 0; net < a.nets; ++net) {
     const float* b0 = a.acc[net] + acc_bias_off(0);
     const float* b3 = a.acc[net] + acc_bias_off(3);
-    for (int n = 0; n < 256; ++n) {
+    for (int n = c * 32; n < c * 32 + 32; ++n) {
       s = fmaf(a.w0[net][n * 171 + kDimXyz + kDimExpr + j], b0[n], s);
       s = fmaf(a.w3[net][(size_t)n * 427 + kDimXyz + kDimExpr + j], b3[n], s);
     }
   }
-  a.out[j] = s;
+  part[c][j] = s;
+  __syncthreads();
+  if (c == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += part[k][j];
+    a.out[j] = t;
+  }
 }
 
 __global__ void cond_kernel(const float* __restrict__ expr, const float* __restrict__ latent, float* __restrict__ cond) {
@@ -836,8 +850,10 @@ cudaError_t launch_chain(const ChainParams& p, int num_sms, cudaStream_t st, lon
 cudaError_t launch_dw(const DwParams& p, int num_sms, cudaStream_t st, long long* launches) {
   const int total = p.n_units * p.t_cnt;
   if (total <= 0) return cudaSuccess;
-  const int grid = total < num_sms ? total : num_sms;
-  dw::dw_kernel<<<grid, dw::kThreads, dw::kSmemBytes, st>>>(p);
+  int parts = num_sms / dw::kGroups;  // CTAs per job group (37 on a 148-SM B200)
+  if (parts > total) parts = total;
+  if (parts < 1) parts = 1;
+  dw::dw_kernel<<<parts * dw::kGroups, dw::kThreads, dw::kSmemBytes, st>>>(p);
   ++*launches;
   return cudaGetLastError();
 }
@@ -860,7 +876,7 @@ cudaError_t launch_latent_grad(const float* const params_c[26], const float* con
   a.nets = params_f ? 2 : 1;
   a.w0[1] = params_f ? params_f[0] : nullptr; a.w3[1] = params_f ? params_f[6] : nullptr; a.acc[1] = acc_f;
   a.out = out;
-  latent_grad_kernel<<<1, 32, 0, st>>>(a);
+  latent_grad_kernel<<<1, 256, 0, st>>>(a);
   ++*launches;
   return cudaGetLastError();
 }

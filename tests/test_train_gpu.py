@@ -1,4 +1,7 @@
-"""Training path: fused forward + gradients, against autograd through the CPU oracle (same noise, same depths)."""
+"""Training path: fused forward + fused backward (nfb_render_backward) through the drop-in API, against autograd through
+the CPU oracle (same noise, same depths).  The backward carries gradients and activations as FP16 tensor-core operands
+(2^-11 relative each) with FP32 accumulation, so parameter gradients are compared at 1e-2 of each tensor's largest
+magnitude (measured: typically 3e-4 .. 2e-3; tests/test_backward_gpu.py checks every stage separately)."""
 import pytest
 import torch
 
@@ -68,10 +71,10 @@ def test_gradients_match_oracle_autograd(built_lib, stress, monkeypatch):
             err = float((p.grad.cpu() - g_ref).abs().max())
             scale = float(g_ref.abs().max()) + 1e-12
             worst = max(worst, err / scale)
-            assert err <= 2e-3 * scale + 1e-7, (k, err, scale)
+            assert err <= 1e-2 * scale + 1e-7, (k, err, scale)
     g_lat = lat.grad.cpu()
     assert float(g_lat[[0, 1, 3]].abs().max()) == 0.0  # only the indexed row receives gradient
-    assert float((g_lat[2] - lat_ref.grad[2]).abs().max()) <= 2e-3 * float(lat_ref.grad[2].abs().max()) + 1e-7
+    assert float((g_lat[2] - lat_ref.grad[2]).abs().max()) <= 1e-2 * float(lat_ref.grad[2].abs().max()) + 1e-7
     print(f"stress={stress}: worst relative gradient error {worst:.2e}")
     nerf.set_precision("fast")
 
