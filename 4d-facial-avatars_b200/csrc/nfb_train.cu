@@ -751,13 +751,8 @@ __global__ void finalize_kernel(const FinArgs a) {
     case 15: v = dbs; break;
     case 16: {  // layers_dir.0.weight[i][j]: j < 256: sum_k dM1[i][k] Wf[j][k] + db6[i] bf[j]; else direction columns
       const int i = e / 280, j = e - i * 280;
-      if (j < 256) {
-        float s = b6[i] * a.p[13][j];
-        for (int k = 0; k < 256; ++k) s = fmaf(acc[kAcc6 + i * 256 + k], a.p[12][j * 256 + k], s);
-        v = s;
-      } else {
-        v = acc[kAcc6d + i * 32 + (j - 256)];
-      }
+      if (j < 256) return;  // written by fin_dir0_kernel (one warp per element, coalesced along k)
+      v = acc[kAcc6d + i * 32 + (j - 256)];
       break;
     }
     case 17: v = b6[e]; break;
@@ -770,6 +765,21 @@ __global__ void finalize_kernel(const FinArgs a) {
     default: break;
   }
   a.g[t][e] = v;
+}
+
+// layers_dir.0.weight[i][j], j < 256:  sum_k dM1[i][k] Wf[j][k] + db6[i] bf[j].  One warp per output element, lanes along k.
+__global__ void fin_dir0_kernel(const FinArgs a) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= 128 * 256) return;
+  const int i = w >> 8, j = w & 255;
+  const float* dm1 = a.acc + kAcc6 + i * 256;
+  const float* wf = a.p[12] + j * 256;
+  float s = 0.f;
+#pragma unroll
+  for (int k = lane; k < 256; k += 32) s = fmaf(dm1[k], wf[k], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) a.g[16][i * 280 + j] = s + a.acc[acc_bias_off(6) + i] * a.p[13][j];
 }
 
 // d latent[j] = sum over networks, n of W0[n][139 + j] db0[n] + W3[n][139 + j] db3[n]
@@ -865,6 +875,8 @@ cudaError_t launch_finalize(const float* const params[26], float* const grads[26
   a.acc = acc;
   a.cond = cond;
   finalize_kernel<<<dim3((256 * 427 + 255) / 256, 26), 256, 0, st>>>(a);
+  ++*launches;
+  fin_dir0_kernel<<<128 * 256 * 32 / 256, 256, 0, st>>>(a);
   ++*launches;
   return cudaGetLastError();
 }
