@@ -66,15 +66,7 @@ constexpr int kOffDirBias = kOffSort + kRowsMax * 4;
 constexpr int kRayFloats = 40;  // o[3] d[3] dnorm valid bg[3] pad PEd[24] ... (see RayP)
 constexpr int kOffRay = kOffDirBias + 2 * 128 * 4;
 constexpr int kOffBars = kOffRay + 2 * kRayFloats * 4;
-#ifndef NFB_GATES
-#define NFB_GATES 2
-#endif
-// Epilogue -> MMA hand-off granularity.  2: the accumulator is converted and signalled in two 128-column halves.
-// 4: in four 64-column quarters (= one K atom of the next step each); the two threads of a row then convert 32 columns
-// per gate, so the next step's first MMAs start after a quarter of the epilogue instead of half of it.
-constexpr int kGates = NFB_GATES;
-static_assert(kGates == 2 || kGates == 4, "NFB_GATES must be 2 or 4");
-constexpr int kNumBars = 2 * kNumSlots + kGates + 2;
+constexpr int kNumBars = 2 * kNumSlots + 4;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kMaxProg = 40;                     // weight units per tile (32 with the current step table)
 constexpr int kSmemBytes = kOffTmemPtr + 16;
@@ -84,9 +76,7 @@ static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0, "ali
 // far too slow for the issue loops):  x = instruction descriptor, y = accumulator column | A column << 16 (TMEM columns
 // relative to the allocation base), z = flags, w = (byte offset in the x1 weight stream) / 16 | rows << 20.
 enum : uint32_t {
-  kUnitFromPe = 1u, kUnitWait0 = 2u, kUnitWait1 = 4u, kUnitFirst = 8u, kUnitCommit0 = 16u, kUnitCommit1 = 32u, kUnitPostWait1 = 64u,
-  kUnitWaitShift = 8,   // 4-gate mode: bits 8..11 = wait for gate g before issuing this unit
-  kUnitPostShift = 12   // 4-gate mode: bits 12..15 = consume gate g after the step's last unit (gate unused by the step)
+  kUnitFromPe = 1u, kUnitWait0 = 2u, kUnitWait1 = 4u, kUnitFirst = 8u, kUnitCommit0 = 16u, kUnitCommit1 = 32u, kUnitPostWait1 = 64u
 };
 constexpr int total_units() {
   int n = 0;
@@ -123,14 +113,6 @@ constexpr ProgTable make_prog() {
       if (first_of_half) flags |= kUnitFirst;
       if (ui.last) flags |= kUnitCommit0;                               // the step's accumulator is complete
       if (u == nu - 1 && !any_g2) flags |= kUnitPostWait1;           // still consume the half-1 "converted" signal
-      {  // 4-gate mode: gate g = "K atom g of this step's TMEM operand is converted" (gate 0 also covers the PE buffer)
-        const int hid = u - si.pe_first;
-        const int hc = si.k_atoms - si.pe_first;  // hidden (TMEM) atoms of the step
-        if (u == 0) flags |= 1u << (kUnitWaitShift + 0);
-        else if (hid >= 1) flags |= 1u << (kUnitWaitShift + hid);
-        if (u == nu - 1)
-          for (int g = (hc > 1 ? hc : 1); g < 4; ++g) flags |= 1u << (kUnitPostShift + g);
-      }
       const uint32_t d_col = region_col_c(s);
       const uint32_t a_col = (region_col_c(s) ^ 256u) + (uint32_t)(ui.ka - si.pe_first) * 64u;
       t.e[i].x = umma_idesc_f16(kTileM, ui.rows);
@@ -252,18 +234,6 @@ __device__ __forceinline__ void epi_half(uint32_t t_slice, uint32_t bias, uint32
   }
 }
 
-// 4-gate variant: one 32-column chunk; hi goes to its first 16 columns, lo (exact mode) to the next 16.
-template <bool EXACT>
-__device__ __forceinline__ void epi_quarter(uint32_t t_chunk, uint32_t bias, uint32_t extra, float* __restrict__ dump,
-                                            uint32_t (&h)[16]) {
-  uint32_t v[32], l[16];
-  tmem_ld32(t_chunk, v);
-  tmem_wait_ld();
-  epi_math<EXACT>(v, bias, extra, dump, h, l);
-  tmem_st16(t_chunk, h);
-  if constexpr (EXACT) tmem_st16(t_chunk + 16, l);
-}
-
 // ReLU mask of 32 post-activation FP16 values (bit j = feature j is non-zero).  An activation that is positive in FP32
 // but rounds to FP16 zero counts as inactive: its value is what the next layer saw.
 __device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&h)[16]) {
@@ -356,8 +326,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 
   const uint32_t bar_full = smem_base + kOffBars;               // [kNumSlots]
   const uint32_t bar_empty = bar_full + kNumSlots * 8;          // [kNumSlots]
-  const uint32_t bar_aready = bar_empty + kNumSlots * 8;        // [kGates] part g of the previous step's output converted
-  const uint32_t bar_accfull = bar_aready + kGates * 8;         // [2] all MMAs of the current step completed ([0] used)
+  const uint32_t bar_aready = bar_empty + kNumSlots * 8;        // [2] half-h output of the previous step converted
+  const uint32_t bar_accfull = bar_aready + 16;                 // [2] all MMAs of the current step completed ([0] used)
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
 
@@ -366,8 +336,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
       mbar_init(bar_full + i * 8, 1);
       mbar_init(bar_empty + i * 8, kCluster);  // released by the MMA warp of every CTA of the cluster
     }
-    for (int h = 0; h < kGates; ++h) mbar_init(bar_aready + h * 8, kRowThreads / 32);  // one arrival per row warp per step
-    for (int h = 0; h < 2; ++h) mbar_init(bar_accfull + h * 8, 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_aready + h * 8, kRowThreads / 32);  // one arrival per row warp per step
+      mbar_init(bar_accfull + h * 8, 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -437,24 +409,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           for (int i = 0; i < kTileUnits; ++i) {
             const ProgEntry e = c_prog.e[i];
             if (prof_on) { const long long tn = clock64(); acc_issue += tn - tq; tq = tn; }
-            if constexpr (kGates == 2) {
-              if (e.z & kUnitWait0) {  // group-1 units: previous step's half-0 output (or the PE buffer) is in place
-                mbar_wait(bar_aready, ph_a0);
-                ph_a0 ^= 1;
-                tc_fence_after_sync();
-              }
-              if (e.z & kUnitWait1) {  // group-2 units: previous step's half-1 output is converted too
-                mbar_wait(bar_aready + 8, ph_a1);
-                ph_a1 ^= 1;
-                tc_fence_after_sync();
-              }
-            } else {  // every gate is used exactly once per step, so one parity bit (ph_a0) serves all four
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                if ((e.z >> (kUnitWaitShift + g)) & 1u) {
-                  mbar_wait(bar_aready + g * 8, ph_a0);
-                  tc_fence_after_sync();
-                }
+            if (e.z & kUnitWait0) {  // group-1 units: previous step's half-0 output (or the PE buffer) is in place
+              mbar_wait(bar_aready, ph_a0);
+              ph_a0 ^= 1;
+              tc_fence_after_sync();
+            }
+            if (e.z & kUnitWait1) {  // group-2 units: previous step's half-1 output is converted too
+              mbar_wait(bar_aready + 8, ph_a1);
+              ph_a1 ^= 1;
+              tc_fence_after_sync();
             }
             if (prof_on) { const long long tn = clock64(); acc_gate += tn - tq; tq = tn; }
             const uint32_t d_tmem = tmem_base + (e.y & 0xFFFFu);
@@ -475,11 +438,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                     umma_ss(d_tmem, pe_desc_hi + (uint64_t)(ks * 2), bd, e.x, acc_flag);
                     if (EXACT && part == 0) umma_ss(d_tmem, pe_desc_lo + (uint64_t)(ks * 2), bd, e.x, 1);
                   } else {
-                    // K-step ks of the atom: 2 gates: 8 columns apart, lo 32 further; 4 gates: the two threads of a row
-                    // each leave 32 K elements at the start of their 32-column chunk, lo 16 columns further.
-                    const uint32_t a_ks = (kGates == 2) ? a_tmem + ks * 8 : a_tmem + (ks >> 1) * 32 + (ks & 1) * 8;
-                    umma_ts(d_tmem, a_ks, bd, e.x, acc_flag);
-                    if (EXACT && part == 0) umma_ts(d_tmem, a_ks + (kGates == 2 ? 32 : 16), bd, e.x, 1);
+                    umma_ts(d_tmem, a_tmem + ks * 8, bd, e.x, acc_flag);
+                    if (EXACT && part == 0) umma_ts(d_tmem, a_tmem + 32 + ks * 8, bd, e.x, 1);
                   }
                 }
                 umma_commit_multicast(bar_empty + slot * 8, kAllCtas);  // slot free here -> tell every loader
@@ -491,16 +451,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               __syncwarp();
               if (++slot == NSLOT) { slot = 0; phase ^= 1; }
             }
-            if constexpr (kGates == 2) {
-              if (e.z & kUnitPostWait1) {
-                mbar_wait(bar_aready + 8, ph_a1);
-                ph_a1 ^= 1;
-              }
-            } else {
-#pragma unroll
-              for (int g = 1; g < 4; ++g)
-                if ((e.z >> (kUnitPostShift + g)) & 1u) mbar_wait(bar_aready + g * 8, ph_a0);
-              if (e.z & kUnitCommit0) ph_a0 ^= 1;  // last unit of the step
+            if (e.z & kUnitPostWait1) {
+              mbar_wait(bar_aready + 8, ph_a1);
+              ph_a1 ^= 1;
             }
           }
         }
@@ -726,8 +679,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           }
           __syncwarp();
           if (lane == 0) {  // PE buffer of tile t is in place (fenced inside prologue): both gates of step 0
-#pragma unroll
-            for (int g = 0; g < kGates; ++g) mbar_arrive(bar_aready + g * 8);
+            mbar_arrive(bar_aready);
+            mbar_arrive(bar_aready + 8);
           }
           if (t == 0) {
             // per-ray additive term of layers_dir.0: W[:, 256:280] . PE_dir (one output feature x ray per thread),
@@ -751,42 +704,6 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             ph_acc0 ^= 1;
             tc_fence_after_sync();
             tm.lap(10 + s);
-            if constexpr (kGates == 4) {
-              if (s <= 8) {  // ReLU layers, four gates: this thread converts columns [64 g + 32 ch, +32) for gate g
-                const int nconv = (s <= 5) ? 4 : 2;  // steps 6..8 are 128 wide (step 6: + sigma in column 128)
-                if (s == 6 && t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias written by all threads
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  uint32_t h[16];
-                  const int c0 = 64 * g + 32 * ch;
-                  if (g < nconv) {
-                    const uint32_t extra = (s == 6) ? smem_u32(dirbias + r * 128 + c0) : 0u;
-                    epi_quarter<EXACT>(t_acc + c0, smem_u32(bias_n + si.bias_off + c0), extra, dump ? dump + c0 : nullptr, h);
-                    tmem_wait_st();
-                  } else if (s == 6 && g == 2 && ch == 0) {  // sigma = column 128 of the folded layers_dir.0 | fc_alpha step
-                    uint32_t v[4];
-                    tmem_ld4(t_acc + 128, v);
-                    tmem_wait_ld();
-                    sigma_raw = __uint_as_float(v[0]) + bias_n[si.bias_off + 128];
-                  }
-                  tc_fence_before_sync();
-                  __syncwarp();
-                  if (lane == 0) mbar_arrive(bar_aready + g * 8);
-                  if constexpr (SAVE) {  // after the gate: the record stores overlap the tensor-core work
-                    if (rec && g < nconv) {
-                      store_t32(rec + rec_x_off(s) + img_row_base(rec_width(s), row), row, c0, h);
-                      reinterpret_cast<uint32_t*>(rec + kRecMask)[(s * 128 + row) * 8 + (c0 >> 5)] = relu_mask32(h);
-                    }
-                  }
-                }
-                tm.lap(20 + s);
-                if (s == 3 && t + 1 < n_tiles) {  // PE buffer is free: encode the next tile under steps 4..9
-                  prologue(t + 1);
-                  tm.lap(2);
-                }
-                continue;
-              }
-            }
             uint32_t ha[16], hb[16];  // FP16 activations of this thread's slice (written to the record in SAVE mode)
             if (s <= 8) {  // ReLU layers: this thread converts output columns [64*ch, 64*ch+64) of the half in place
               const int c0 = 64 * ch;
