@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -34,6 +35,7 @@ struct NfbHandle {
   int num_sms = 0;
   nfb::NetBuffers net[2];
   bool frame_set = false;
+  bool use_render2 = true;
   long long launches = 0;
   // cached torch.linspace(0,1,n) tables on the device
   float* lin_c = nullptr; int lin_c_n = 0;
@@ -130,6 +132,11 @@ int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
   NFB_CUDA(dev_alloc(&h->d_expr, nfb::kDimExpr));
   NFB_CUDA(dev_alloc(&h->d_latent, nfb::kDimLatent));
   NFB_CUDA(nfb::render_kernel_setup());
+  NFB_CUDA(nfb::render2_kernel_setup());
+  {  // NFB_KERNEL=v4 forces the one-tile-in-flight kernel everywhere (default: the two-tile kernel where it applies)
+    const char* k = std::getenv("NFB_KERNEL");
+    h->use_render2 = !(k && std::strcmp(k, "v4") == 0);
+  }
   *out = h;
   return NFB_OK;
 }
@@ -277,7 +284,11 @@ static int render_impl(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm,
     tr.n_rays = rays->n_rays; tr.nc = nc; tr.nf = nf; tr.rays_per_unit = p.rays_per_unit; tr.tiles_c = p.tiles_c;
     tr.tiles_f = p.tiles_f; tr.n_units = p.n_units; tr.has_bg = rays->background != nullptr; tr.white_bkgd = p.white_bkgd;
   }
-  NFB_CUDA(nfb::launch_render(p, exact ? 1 : 0, h->num_sms, st, &h->launches));
+  // fast evaluation runs the two-tiles-in-flight kernel; exact mode (hi+lo operands need twice the TMEM columns), the
+  // training forward (records) and the debug probes run the one-tile kernel
+  const bool two_tile = h->use_render2 && !exact && !train && !p.dbg_act && !p.prof;
+  if (two_tile) NFB_CUDA(nfb::launch_render2(p, h->num_sms, st, &h->launches));
+  else NFB_CUDA(nfb::launch_render(p, exact ? 1 : 0, h->num_sms, st, &h->launches));
   if (train) h->tr.valid = true;
   return NFB_OK;
 }

@@ -99,5 +99,8 @@ cudaError_t launch_frame_fold(NetBuffers& nb, const float* expr, const float* la
 // precision: 0 = fast (x1), 1 = exact (x3).  num_sms = CTAs to launch at most.
 cudaError_t launch_render(const RenderParams& p, int precision, int num_sms, cudaStream_t st, long long* launches);
 cudaError_t render_kernel_setup();  // opt-in to the large dynamic shared memory size
+// Two-tiles-in-flight kernel (nfb_render2.cu): fast mode, evaluation (no training records, no layer probe / phase timers).
+cudaError_t render2_kernel_setup();
+cudaError_t launch_render2(const RenderParams& p, int num_sms, cudaStream_t st, long long* launches);
 
 }  // namespace nfb

@@ -1,0 +1,662 @@
+// nfb_render2.cu — the render path with TWO tiles in flight per SM (fast mode, evaluation).
+//
+// Same reference path and same per-tile algebra as nfb_render.cu (see its header for the reference citations); what
+// changes is how the tensor core is kept busy.  With one tile per SM the epilogue -> MMA hand-off of every step is
+// exposed (the tensor pipe is busy about a third of the time).  Here every CTA runs two tile "streams" X and Y in lock
+// step, and every MLP step is issued as N=128 half-steps in the order  X.h0  Y.h0  X.h1  Y.h1 :
+//
+//   * TMEM (512 columns): stream x owns P_x = [256x, 256x+128): the FP16 A operand (K <= 256 = 4 atoms of 32 columns) and
+//     Q_x = [256x+128, 256x+256): the FP32 accumulator of one half-step (N = 128).  Both halves of a step read P_x, so
+//     the half-0 result is converted to FP16 and HELD IN REGISTERS (32 per thread) until the half-1 MMAs have finished
+//     reading P_x; then the epilogue of half 1 stores both halves into P_x — the operand of the next step.  No shared
+//     memory is spent on activations.
+//   * While the row warps convert X.h0, the tensor core runs Y.h0; while they convert Y.h0 it runs X.h1; and so on: each
+//     epilogue has one half-step (16 MMAs) of the other stream to hide under.
+//   * Both streams use the same weights back to back, so a weight half-unit ([128 rows x 64 K] = 16 KB, a contiguous
+//     half of the unit the packed stream already holds) is loaded ONCE per tile pair: L2 -> SM weight traffic per tile
+//     halves.  Ring = 8 slots x 16 KB; a slot is released (cluster-multicast commit) after stream Y has used it.
+//
+// A unit of work is 2R rays (R = 2, or 1 when one ray fills the pass): rays [0,R) form stream X, rays [R,2R) stream Y;
+// sampling, compositing, inverse-CDF resampling and the sort run for all 2R rays between the passes as in nfb_render.cu.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "nfb_internal.h"
+#include "nfb_layout.h"
+#include "nfb_ptx.cuh"
+#include "nfb_render_common.cuh"
+
+namespace nfb {
+namespace v6 {
+
+constexpr int kNumSlots = 8;
+constexpr int kSlotBytes = 16384;
+constexpr int kRowsMax = 512;  // sample rows of one pass of one stream
+constexpr int kThreads = 320;  // producer warp + MMA warp + 8 row warps
+constexpr int kCluster = 2;
+constexpr int kRowThreads = 256;
+constexpr uint32_t kRowBarrier = 1;
+
+// shared memory map
+constexpr int kOffRing = 0;
+constexpr int kOffPe = kOffRing + kNumSlots * kSlotBytes;     // [2 streams][128 rows x 128 B]
+constexpr int kOffBias = kOffPe + 2 * kTileM * 128;
+constexpr int kOffRaw = kOffBias + 2 * kBiasFloats * 4;       // [2][kRowsMax] float4
+constexpr int kOffZ = kOffRaw + 2 * kRowsMax * 16;
+constexpr int kOffW = kOffZ + 2 * kRowsMax * 4;
+constexpr int kOffCdf = kOffW + 2 * kRowsMax * 4;
+constexpr int kOffBins = kOffCdf + 2 * kRowsMax * 4;
+constexpr int kOffSort = kOffBins + 2 * kRowsMax * 4;
+constexpr int kOffDirBias = kOffSort + 2 * kRowsMax * 4;      // [4 rays][128]
+constexpr int kOffRay = kOffDirBias + 4 * 128 * 4;
+constexpr int kOffBars = kOffRay + 4 * kRayFloats * 4;
+constexpr int kNumBars = 2 * kNumSlots + 4;                   // full[8] empty[8] gate[2] accfull[2]
+constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmemPtr + 16;
+static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0, "alignment");
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+
+// Half-steps.  Step s (nfb_layout.h) has 1 or 2 halves; half h covers weight rows [h * nh0, h * nh0 + N_h).
+__host__ __device__ constexpr int num_halves(int s) { return step_info(s).nh1 > 0 ? 2 : 1; }
+__host__ __device__ constexpr int half_rows(int s, int h) { return h ? step_info(s).nh1 : step_info(s).nh0; }
+
+enum : uint32_t { kFromPe = 1u, kFirst = 2u, kLast = 4u };
+struct ProgEntry { uint32_t x, y, z, w; };  // x: idesc; y: A column (relative to P); z: flags; w: (src offset / 16) | rows << 20
+struct Group { uint16_t first, count; };
+constexpr int kMaxProg = 64, kMaxGroups = 20;
+struct ProgTable { ProgEntry e[kMaxProg]; Group g[kMaxGroups]; int n_entries, n_groups; };
+constexpr ProgTable make_prog() {
+  ProgTable t{};
+  int i = 0, g = 0;
+  for (int s = 0; s < kNumSteps; ++s) {
+    const StepInfo si = step_info(s);
+    for (int h = 0; h < num_halves(s); ++h, ++g) {
+      t.g[g].first = (uint16_t)i;
+      t.g[g].count = (uint16_t)si.k_atoms;
+      const int rows = half_rows(s, h);
+      for (int u = 0; u < si.k_atoms; ++u, ++i) {
+        uint32_t flags = 0;
+        if (si.pe_first && u == 0) flags |= kFromPe;
+        if (u == 0) flags |= kFirst;
+        if (u == si.k_atoms - 1) flags |= kLast;
+        t.e[i].x = umma_idesc_f16(kTileM, rows);
+        t.e[i].y = (uint32_t)(u - si.pe_first) * 32u;  // K atom a of the TMEM operand = P + 32 a (unused for the PE atom)
+        t.e[i].z = flags;
+        t.e[i].w = ((uint32_t)(step_offset_x1(s) + unit_offset_in_step(s, u) + h * si.nh0 * 128) >> 4) | ((uint32_t)rows << 20);
+      }
+    }
+  }
+  t.n_entries = i;
+  t.n_groups = g;
+  return t;
+}
+constexpr ProgTable kProgHost = make_prog();
+static_assert(kProgHost.n_entries <= kMaxProg && kProgHost.n_groups <= kMaxGroups, "program table too small");
+constexpr int kNumGroups = kProgHost.n_groups;    // 17
+constexpr int kNumEntries = kProgHost.n_entries;  // 58
+__constant__ ProgTable c_prog = make_prog();
+
+// Accumulator chunk -> bias, ReLU, FP16: this thread's 64 columns of the half-step as 32 packed words.
+__device__ __forceinline__ void epi_load64(uint32_t t_q, uint32_t bias, uint32_t extra, uint32_t (&h)[32]) {
+  uint32_t va[32], vb[32], ha[16], hb[16], lo[16];
+  tmem_ld32(t_q, va);
+  tmem_ld32(t_q + 32, vb);
+  tmem_wait_ld();
+  epi_math<false>(va, bias, extra, nullptr, ha, lo);
+  epi_math<false>(vb, bias + 128, extra ? extra + 128 : 0u, nullptr, hb, lo);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { h[j] = ha[j]; h[16 + j] = hb[j]; }
+}
+__device__ __forceinline__ void store32(uint32_t t_p, const uint32_t (&h)[32]) {
+  uint32_t a[16], b[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { a[j] = h[j]; b[j] = h[16 + j]; }
+  tmem_st16(t_p, a);
+  tmem_st16(t_p + 16, b);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_constant__ RenderParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  if ((smem_base & 1023u) != 0u) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t bar_full = smem_base + kOffBars;            // [kNumSlots]
+  const uint32_t bar_empty = bar_full + kNumSlots * 8;       // [kNumSlots]
+  const uint32_t bar_gate = bar_empty + kNumSlots * 8;       // [2] stream x: operand / accumulator ready for its next half-step
+  const uint32_t bar_accfull = bar_gate + 16;                // [2] stream x: half-step accumulator complete
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+  float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNumSlots; ++i) {
+      mbar_init(bar_full + i * 8, 1);
+      mbar_init(bar_empty + i * 8, kCluster);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(bar_gate + x * 8, kRowThreads / 32);
+      mbar_init(bar_accfull + x * 8, 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_base + kOffTmemPtr, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kBiasFloats; i += kThreads) {
+    bias_s[i] = p.bias[0][i];
+    bias_s[kBiasFloats + i] = (p.nf > 0) ? p.bias[1][i] : 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t cta_rank = cluster_ctarank();
+  constexpr uint16_t kAllCtas = (1u << kCluster) - 1;
+
+  const int first_in_cluster = (int)blockIdx.x - (int)cta_rank;
+  const int n_iter = (p.n_units - first_in_cluster + (int)gridDim.x - 1) / (int)gridDim.x;  // n_units = super-units of 2R rays
+  const int tiles_per_unit = p.tiles_c + p.tiles_f;  // tile PAIRS per super-unit
+
+  if (warp == 0) {
+    // ============================== weight producer ==============================
+    uint32_t slot = 0, phase = 0, seq = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      for (int t = 0; t < tiles_per_unit; ++t) {
+        const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
+        for (int i = 0; i < kNumEntries; ++i) {
+          const uint32_t w = c_prog.e[i].w;
+          const uint32_t off = (w & 0xFFFFFu) << 4, bytes = (w >> 20) * 128u;
+          mbar_wait(bar_empty + slot * 8, phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
+            if ((seq % kCluster) == cta_rank)
+              bulk_g2s_multicast(smem_base + kOffRing + slot * kSlotBytes, base + off, bytes, bar_full + slot * 8, kAllCtas);
+          }
+          __syncwarp();
+          ++seq;
+          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    uint32_t slot = 0, phase = 0;  // ring position at the start of the current group
+    uint32_t ph_gate0 = 0, ph_gate1 = 0;
+    const uint64_t pe_desc0 = umma_smem_desc_sw128(smem_base + kOffPe);
+    const uint64_t pe_desc1 = umma_smem_desc_sw128(smem_base + kOffPe + kTileM * 128);
+    for (int it = 0; it < n_iter; ++it) {
+      for (int t = 0; t < tiles_per_unit; ++t) {
+        for (int g = 0; g < kNumGroups; ++g) {
+          const uint32_t g_first = c_prog.g[g].first, g_count = c_prog.g[g].count;
+          uint32_t sl = slot, ph = phase;
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            // stream x may run this half-step: its operand P_x is in place and its accumulator Q_x has been read
+            if (x == 0) { mbar_wait(bar_gate, ph_gate0); ph_gate0 ^= 1; }
+            else        { mbar_wait(bar_gate + 8, ph_gate1); ph_gate1 ^= 1; }
+            tc_fence_after_sync();
+            sl = slot; ph = phase;  // both streams walk the same ring slots
+            const uint32_t p_tmem = tmem_base + (uint32_t)x * 256u;
+            const uint32_t q_tmem = p_tmem + 128u;
+            const uint64_t pe_desc = x ? pe_desc1 : pe_desc0;
+            for (uint32_t j = 0; j < g_count; ++j) {
+              const ProgEntry e = c_prog.e[g_first + j];
+              mbar_wait(bar_full + sl * 8, ph);  // stream Y finds the slot already filled
+              tc_fence_after_sync();
+              const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + sl * kSlotBytes);
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t bd = b_desc + (uint64_t)(ks * 2);
+                  const uint32_t acc_flag = ((e.z & kFirst) && ks == 0) ? 0u : 1u;
+                  if (e.z & kFromPe) umma_ss(q_tmem, pe_desc + (uint64_t)(ks * 2), bd, e.x, acc_flag);
+                  else umma_ts(q_tmem, p_tmem + e.y + ks * 8, bd, e.x, acc_flag);
+                }
+                if (x == 1) umma_commit_multicast(bar_empty + sl * 8, kAllCtas);  // both streams are done with the slot
+                if (e.z & kLast) umma_commit(bar_accfull + x * 8);
+              }
+              __syncwarp();
+              if (++sl == kNumSlots) { sl = 0; ph ^= 1; }
+            }
+          }
+          slot = sl; phase = ph;
+        }
+      }
+    }
+  } else {
+    // ============================== row warps ==============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ch = (warp - 2) >> 2;
+    const int ew = warp - 2;
+    const int etid = ch * 128 + row;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    float4* carry_raw = reinterpret_cast<float4*>(smem + kOffRaw);  // [x * kRowsMax + prow]
+    float* carry_z = reinterpret_cast<float*>(smem + kOffZ);
+    float* scr_w = reinterpret_cast<float*>(smem + kOffW);
+    float* scr_cdf = reinterpret_cast<float*>(smem + kOffCdf);
+    float* scr_bins = reinterpret_cast<float*>(smem + kOffBins);
+    float* scr_sort = reinterpret_cast<float*>(smem + kOffSort);
+    float* dirbias = reinterpret_cast<float*>(smem + kOffDirBias);
+    RayP* rayp = reinterpret_cast<RayP*>(smem + kOffRay);
+    const int R = p.rays_per_unit;   // rays per stream
+    const int RR = 2 * R;            // rays per unit of work
+    const bool has_bg = p.bg != nullptr;
+    uint32_t ph_acc0 = 0, ph_acc1 = 0;
+
+    for (int it = 0; it < n_iter; ++it) {
+      const int unit = blockIdx.x + it * gridDim.x;
+      // ---- per-ray constants (ray slot qy = x * R + r)
+      if (etid < RR) {
+        RayP& rp = rayp[etid];
+        const int g = unit * RR + etid;
+        rp.valid = g < p.n_rays;
+        rp.gidx = g;
+        if (rp.valid) {
+          float o0, o1, o2, d0, d1, d2;
+          if (p.o) {
+            o0 = p.o[3 * g]; o1 = p.o[3 * g + 1]; o2 = p.o[3 * g + 2];
+            d0 = p.d[3 * g]; d1 = p.d[3 * g + 1]; d2 = p.d[3 * g + 2];
+          } else {  // get_ray_bundle (nerf_helpers.py:111-122), same operation order in FP32
+            const int pj = p.row_begin + g / p.width, pi = g % p.width;
+            const float cx = __fdiv_rn(__fsub_rn((float)pi, p.wcx), p.fx);
+            const float cy = -__fdiv_rn(__fsub_rn((float)pj, p.hcy), p.fy);
+            d0 = __fadd_rn(__fadd_rn(__fmul_rn(cx, p.pose[0]), __fmul_rn(cy, p.pose[1])), __fmul_rn(-1.f, p.pose[2]));
+            d1 = __fadd_rn(__fadd_rn(__fmul_rn(cx, p.pose[4]), __fmul_rn(cy, p.pose[5])), __fmul_rn(-1.f, p.pose[6]));
+            d2 = __fadd_rn(__fadd_rn(__fmul_rn(cx, p.pose[8]), __fmul_rn(cy, p.pose[9])), __fmul_rn(-1.f, p.pose[10]));
+            o0 = p.pose[3]; o1 = p.pose[7]; o2 = p.pose[11];
+          }
+          rp.o[0] = o0; rp.o[1] = o1; rp.o[2] = o2;
+          rp.d[0] = d0; rp.d[1] = d1; rp.d[2] = d2;
+          rp.dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+          if (has_bg) { rp.bg[0] = p.bg[3 * g]; rp.bg[1] = p.bg[3 * g + 1]; rp.bg[2] = p.bg[3 * g + 2]; }
+          rp.dz = p.dir_z ? p.dir_z[g] : d2;
+        } else {
+          for (int k = 0; k < 3; ++k) { rp.o[k] = 0.f; rp.d[k] = 0.f; rp.bg[k] = 0.f; }
+          rp.dnorm = 0.f;
+          rp.dz = 0.f;
+        }
+      }
+      named_bar_sync(kRowBarrier, kRowThreads);
+      if (etid < RR * 12) {  // direction encoder input (d_z, near, far), train_utils.py:14
+        const int rr = etid / 12, k = etid - rr * 12, f = k / 3, c = k - f * 3;
+        RayP& rp = rayp[rr];
+        const float v = (c == 0) ? rp.dz : (c == 1 ? p.near_ : p.far_);
+        float sn, cs;
+        sincosf(v * (float)(1 << f), &sn, &cs);
+        rp.ped[6 * f + c] = rp.valid ? sn : 0.f;
+        rp.ped[6 * f + 3 + c] = rp.valid ? cs : 0.f;
+      }
+      named_bar_sync(kRowBarrier, kRowThreads);
+
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && p.nf == 0) break;
+        const int S = pass ? p.s_fine : p.nc;
+        const int rows = R * S;  // rows of one stream in this pass
+        const int n_tiles = pass ? p.tiles_f : p.tiles_c;
+        const float* bias_n = bias_s + pass * kBiasFloats;
+
+        // ---- sample depth + positional encoding of tile t of stream x -> PE buffer x
+        auto prologue = [&](int x, int t) {
+          const int prow = t * 128 + row;
+          const bool live = prow < rows;
+          const int r = live ? prow / S : 0;
+          const int i = live ? prow - r * S : 0;
+          const RayP& rp = rayp[x * R + r];
+          float z = 0.f;
+          if (live) {
+            if (pass == 0) {
+              const float tc = p.t_coarse[i];
+              z = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tc)), __fmul_rn(p.far_, tc));
+              if (p.perturb) {  // stratified jitter (train_utils.py:69-76)
+                float lower = z, upper = z;
+                if (i > 0) {
+                  const float tp = p.t_coarse[i - 1];
+                  const float zp = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tp)), __fmul_rn(p.far_, tp));
+                  lower = __fmul_rn(0.5f, __fadd_rn(z, zp));
+                }
+                if (i < S - 1) {
+                  const float tn = p.t_coarse[i + 1];
+                  const float zn = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tn)), __fmul_rn(p.far_, tn));
+                  upper = __fmul_rn(0.5f, __fadd_rn(zn, z));
+                }
+                const float tr = rp.valid ? p.t_rand[(size_t)rp.gidx * p.nc + i] : 0.f;
+                z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
+              }
+              if (ch == 0) carry_z[x * kRowsMax + prow] = z;
+            } else {
+              z = carry_z[x * kRowsMax + prow];
+            }
+          }
+          const float px = __fadd_rn(rp.o[0], __fmul_rn(rp.d[0], z));
+          const float py = __fadd_rn(rp.o[1], __fmul_rn(rp.d[1], z));
+          const float pz = __fadd_rn(rp.o[2], __fmul_rn(rp.d[2], z));
+          float f[32];
+          if (ch == 0) {  // lanes 0..31: xyz, frequencies 0..3, sin of frequency 4, cos(x), cos(y) of frequency 4
+            f[0] = px; f[1] = py; f[2] = pz;
+#pragma unroll
+            for (int fr = 0; fr < 4; ++fr) {
+              const float sc = (float)(1 << fr);
+              pe_sincos<false>(px * sc, f[3 + 6 * fr + 0], f[3 + 6 * fr + 3]);
+              pe_sincos<false>(py * sc, f[3 + 6 * fr + 1], f[3 + 6 * fr + 4]);
+              pe_sincos<false>(pz * sc, f[3 + 6 * fr + 2], f[3 + 6 * fr + 5]);
+            }
+            float cz;
+            pe_sincos<false>(px * 16.f, f[27], f[30]);
+            pe_sincos<false>(py * 16.f, f[28], f[31]);
+            pe_sincos<false>(pz * 16.f, f[29], cz);
+          } else {        // lanes 32..63: cos(z) of frequency 4, frequencies 5..9, zero pad
+            float sz;
+            pe_sincos<false>(pz * 16.f, sz, f[0]);
+#pragma unroll
+            for (int fr = 5; fr < 10; ++fr) {
+              const float sc = (float)(1 << fr);
+              const int b = 6 * fr - 29;
+              pe_sincos<false>(px * sc, f[b + 0], f[b + 3]);
+              pe_sincos<false>(py * sc, f[b + 1], f[b + 4]);
+              pe_sincos<false>(pz * sc, f[b + 2], f[b + 5]);
+            }
+            f[31] = 0.f;
+          }
+          uint8_t* pe = smem + kOffPe + x * (kTileM * 128);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            uint32_t hi[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hi[e] = pack_f16x2(f[qq * 8 + 2 * e], f[qq * 8 + 2 * e + 1]);
+            const int off = row * 128 + (((ch * 4 + qq) ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(pe + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          }
+          fence_proxy_async_smem();
+        };
+
+        prologue(0, 0);
+        prologue(1, 0);
+        named_bar_sync(kRowBarrier, kRowThreads);  // carry_z of this pass is complete
+
+        for (int t = 0; t < n_tiles; ++t) {
+          const int prow = t * 128 + row;
+          const bool live = prow < rows;
+          const int r = live ? prow / S : 0;
+          const int i = live ? prow - r * S : 0;
+          __syncwarp();
+          if (lane == 0) {  // PE buffers of tile t are in place: first half-step of both streams may start
+            mbar_arrive(bar_gate);
+            mbar_arrive(bar_gate + 8);
+          }
+          if (t == 0) {
+            // per-ray additive term of layers_dir.0: W[:, 256:280] . PE_dir; thread = (output feature `row`, rays ch and ch+2)
+            const float* wt = p.wd0b_t[pass];
+            float acc0 = 0.f, acc1 = 0.f;
+            const RayP& ra = rayp[ch < RR ? ch : 0];
+            const RayP& rb = rayp[ch + 2 < RR ? ch + 2 : 0];
+#pragma unroll 8
+            for (int j = 0; j < kDimDir; ++j) {
+              const float w = wt[j * 128 + row];
+              acc0 = fmaf(w, ra.ped[j], acc0);
+              acc1 = fmaf(w, rb.ped[j], acc1);
+            }
+            dirbias[ch * 128 + row] = acc0;
+            dirbias[(ch + 2) * 128 + row] = acc1;
+          }
+
+          uint32_t keep0[32], keep1[32];  // half-0 results of streams X / Y, held until P is dead
+          float sigma_raw0 = 0.f, sigma_raw1 = 0.f;
+          for (int s = 0; s < kNumSteps; ++s) {
+            const StepInfo si = step_info(s);
+            const int c0 = 64 * ch;
+            if (s == 6 && t == 0) named_bar_sync(kRowBarrier, kRowThreads);  // dirbias written by all threads
+            for (int h = 0; h < num_halves(s); ++h) {
+#pragma unroll
+              for (int x = 0; x < 2; ++x) {
+                const uint32_t t_p = t_lane + (uint32_t)x * 256u;
+                const uint32_t t_q = t_p + 128u;
+                if (x == 0) { mbar_wait(bar_accfull, ph_acc0); ph_acc0 ^= 1; }
+                else        { mbar_wait(bar_accfull + 8, ph_acc1); ph_acc1 ^= 1; }
+                tc_fence_after_sync();
+                uint32_t (&keep)[32] = x ? keep1 : keep0;
+                float& sigma_raw = x ? sigma_raw1 : sigma_raw0;
+                const RayP& rp = rayp[x * R + r];
+                if (s <= 5) {
+                  if (h == 0) {  // outputs [64 ch, +64) of features 0..127 -> registers
+                    epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + c0), 0u, keep);
+                  } else {       // P_x is dead: store half 0 (K atom ch), convert half 1 (K atom 2 + ch)
+                    uint32_t hh[32];
+                    store32(t_p + 32 * ch, keep);
+                    epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + 128 + c0), 0u, hh);
+                    store32(t_p + 64 + 32 * ch, hh);
+                    tmem_wait_st();
+                  }
+                } else if (s == 6) {
+                  if (h == 0) {
+                    epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + c0), smem_u32(dirbias + (x * R + r) * 128 + c0), keep);
+                  } else {  // sigma = column 0 of the 16-wide second half; then g0 becomes the operand (K = 128)
+                    if (ch == 0) {
+                      uint32_t v[4];
+                      tmem_ld4(t_q, v);
+                      tmem_wait_ld();
+                      sigma_raw = __uint_as_float(v[0]) + bias_n[si.bias_off + 128];
+                    }
+                    store32(t_p + 32 * ch, keep);
+                    tmem_wait_st();
+                  }
+                } else if (s <= 8) {  // 128 -> 128 layers: the MMAs that read P have completed
+                  uint32_t hh[32];
+                  epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + c0), 0u, hh);
+                  store32(t_p + 32 * ch, hh);
+                  tmem_wait_st();
+                } else if (ch == 0) {
+                  // fc_rgb output: colour and sigma per sample for compositing (volume_rendering_utils.py:29-33, 41-53)
+                  uint32_t v[4];
+                  tmem_ld4(t_q, v);
+                  tmem_wait_ld();
+                  const float* b = bias_n + si.bias_off;
+                  if (live) {
+                    const float r0 = __uint_as_float(v[0]) + b[0], r1 = __uint_as_float(v[1]) + b[1], r2 = __uint_as_float(v[2]) + b[2];
+                    if (rp.valid) {
+                      float* dr = pass ? p.dbg_raw_f : p.dbg_raw_c;
+                      if (dr) reinterpret_cast<float4*>(dr)[(size_t)rp.gidx * S + i] = make_float4(r0, r1, r2, sigma_raw);
+                    }
+                    float sig = sigma_raw;
+                    if (p.noise_std > 0.f && rp.valid)
+                      sig = __fadd_rn(sig, __fmul_rn((pass ? p.noise_f : p.noise_c)[(size_t)rp.gidx * S + i], p.noise_std));
+                    sig = fmaxf(sig, 0.f);
+                    float4 pre;
+                    if (i == S - 1) {
+                      sig = __fadd_rn(sig, 1e-6f);
+                      if (has_bg) { pre.x = rp.bg[0]; pre.y = rp.bg[1]; pre.z = rp.bg[2]; }
+                    }
+                    if (!(has_bg && i == S - 1)) {
+                      pre.x = 1.f / (1.f + expf(-r0));
+                      pre.y = 1.f / (1.f + expf(-r1));
+                      pre.z = 1.f / (1.f + expf(-r2));
+                    }
+                    pre.w = sig;
+                    carry_raw[x * kRowsMax + prow] = pre;
+                  }
+                }
+                if (s < kNumSteps - 1) {  // Q_x has been read (and, after a step's last half, P_x holds the next operand)
+                  tc_fence_before_sync();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(bar_gate + x * 8);
+                }
+              }
+            }
+            if (s == 3 && t + 1 < n_tiles) {  // both PE buffers are free: encode the next tile pair under steps 4..9
+              prologue(0, t + 1);
+              prologue(1, t + 1);
+            }
+          }
+        }  // tile pairs
+        named_bar_sync(kRowBarrier, kRowThreads);
+
+        // ---- debug dump of the sample depths
+        {
+          float* dz = pass ? p.dbg_z_f : p.dbg_z_c;
+          if (dz) {
+            for (int k = etid; k < RR * S; k += kRowThreads) {
+              const int qy = k / S, ii = k - qy * S;
+              const int x = qy / R, rr = qy - x * R;
+              if (rayp[qy].valid) dz[(size_t)rayp[qy].gidx * S + ii] = carry_z[x * kRowsMax + rr * S + ii];
+            }
+          }
+        }
+
+        // ---- compositing: warp `ew` renders ray slot `ew`
+        if (ew < RR && rayp[ew].valid) {
+          const RayP& rp = rayp[ew];
+          const int g = rp.gidx;
+          const int x = ew / R, rr = ew - x * R;
+          const int base = x * kRowsMax + rr * S;
+          float* o_rgb = pass ? p.rgb_f : p.rgb_c;
+          float* o_disp = pass ? p.disp_f : p.disp_c;
+          float* o_acc = pass ? p.acc_f : p.acc_c;
+          const float wl = composite_ray(carry_raw + base, carry_z + base, scr_w + base, S, rp.dnorm, p.white_bkgd != 0,
+                                         o_rgb ? o_rgb + 3 * (size_t)g : nullptr, o_disp ? o_disp + g : nullptr,
+                                         o_acc ? o_acc + g : nullptr, lane);
+          const bool last_pass = (pass == 1) || (p.nf == 0);
+          if (last_pass && lane == 0 && p.w_last) p.w_last[g] = wl;
+        }
+        if (pass == 1 || p.nf == 0) {
+          named_bar_sync(kRowBarrier, kRowThreads);  // carry buffers are reused by the next unit
+          continue;
+        }
+
+        // ---- inverse-CDF resampling (nerf_helpers.py:344-387) on weights[1:-1] over the mid-point bins
+        __syncwarp();
+        const int nb = p.nc - 1;
+        const int nw = p.nc - 2;
+        if (ew < RR) {
+          const int x = ew / R, rr = ew - x * R;
+          const int base = x * kRowsMax + rr * p.nc;
+          const float* w = scr_w + base;
+          const float* zc = carry_z + base;
+          float* cdf = scr_cdf + base;
+          float* bins = scr_bins + base;
+          for (int k = lane; k < nb; k += 32) bins[k] = __fmul_rn(0.5f, __fadd_rn(zc[k + 1], zc[k]));
+          const int per = (nw + 31) >> 5;
+          const int k0 = lane * per;
+          float part = 0.f;
+          for (int j = 0; j < per; ++j)
+            if (k0 + j < nw) part += __fadd_rn(w[k0 + j + 1], 1e-5f);
+          const float total = warp_sum(part);
+          float psum = 0.f;
+          for (int j = 0; j < per; ++j)
+            if (k0 + j < nw) psum += __fdiv_rn(__fadd_rn(w[k0 + j + 1], 1e-5f), total);
+          float incl = psum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float tt = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += tt;
+          }
+          float run = incl - psum;
+          if (lane == 0) cdf[0] = 0.f;
+          for (int j = 0; j < per; ++j)
+            if (k0 + j < nw) {
+              run += __fdiv_rn(__fadd_rn(w[k0 + j + 1], 1e-5f), total);
+              cdf[k0 + j + 1] = run;
+            }
+        }
+        named_bar_sync(kRowBarrier, kRowThreads);
+        // cat(z_coarse, z_samples) per ray into scr_sort (per stream: stride s_fine)
+        const int SF = p.s_fine;
+        for (int k = etid; k < RR * SF; k += kRowThreads) {
+          const int qy = k / SF, i = k - qy * SF;
+          const int x = qy / R, rr = qy - x * R;
+          float val;
+          if (i < p.nc) {
+            val = carry_z[x * kRowsMax + rr * p.nc + i];
+          } else {
+            const int j = i - p.nc;
+            const float* cdf = scr_cdf + x * kRowsMax + rr * p.nc;
+            const float* bins = scr_bins + x * kRowsMax + rr * p.nc;
+            const float u = p.perturb ? (rayp[qy].valid ? p.u_rand[(size_t)rayp[qy].gidx * p.nf + j] : 0.f) : p.u_fine[j];
+            int lo = 0, hi = nb;  // searchsorted(..., right=True)
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+            }
+            const int below = max(0, lo - 1), above = min(nb - 1, lo);
+            const float cb = cdf[below], ca = cdf[above];
+            float den = __fsub_rn(ca, cb);
+            if (den < 1e-5f) den = 1.f;
+            const float tt = __fdiv_rn(__fsub_rn(u, cb), den);
+            val = __fadd_rn(bins[below], __fmul_rn(tt, __fsub_rn(bins[above], bins[below])));
+          }
+          scr_sort[x * kRowsMax + rr * SF + i] = val;
+        }
+        named_bar_sync(kRowBarrier, kRowThreads);
+        // ---- torch.sort(cat(z, z_samples)) (train_utils.py:126) as a rank merge (see nfb_render.cu)
+        for (int k = etid; k < RR * SF; k += kRowThreads) {
+          const int qy = k / SF, i = k - qy * SF;
+          const int x = qy / R, rr = qy - x * R;
+          const float* zc = scr_sort + x * kRowsMax + rr * SF;
+          const float* zs = zc + p.nc;
+          const float v = zc[i];
+          int rank;
+          if (i < p.nc) {
+            rank = i;
+            for (int j = 0; j < p.nf; ++j) rank += (zs[j] < v) ? 1 : 0;
+          } else {
+            const int jm = i - p.nc;
+            int lo = 0, hi = p.nc;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (zc[mid] <= v) lo = mid + 1; else hi = mid;
+            }
+            rank = lo;
+            for (int j = 0; j < p.nf; ++j) {
+              const float y = zs[j];
+              rank += (y < v || (y == v && j < jm)) ? 1 : 0;
+            }
+          }
+          carry_z[x * kRowsMax + rr * SF + rank] = v;
+        }
+        named_bar_sync(kRowBarrier, kRowThreads);
+      }  // pass
+    }    // units
+    tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace v6
+
+cudaError_t render2_kernel_setup() {
+  return cudaFuncSetAttribute(v6::render2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v6::kSmemBytes);
+}
+
+// `p` is prepared for the one-tile kernel (n_units = units of R rays); here a unit of work is 2R rays.
+cudaError_t launch_render2(const RenderParams& p_in, int num_sms, cudaStream_t st, long long* launches) {
+  RenderParams p = p_in;
+  p.n_units = (p_in.n_rays + 2 * p_in.rays_per_unit - 1) / (2 * p_in.rays_per_unit);
+  int grid = p.n_units < num_sms ? p.n_units : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  grid = (grid + v6::kCluster - 1) / v6::kCluster * v6::kCluster;
+  if (grid > num_sms) grid = num_sms / v6::kCluster * v6::kCluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(v6::kThreads);
+  cfg.dynamicSmemBytes = v6::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = v6::kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, v6::render2_kernel, p);
+  ++*launches;
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+}  // namespace nfb
