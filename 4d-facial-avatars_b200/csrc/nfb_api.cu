@@ -286,7 +286,7 @@ static int render_impl(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm,
   }
   // fast evaluation runs the two-tiles-in-flight kernel; exact mode (hi+lo operands need twice the TMEM columns), the
   // training forward (records) and the debug probes run the one-tile kernel
-  const bool two_tile = h->use_render2 && !exact && !train && !p.dbg_act && !p.prof;
+  const bool two_tile = h->use_render2 && !exact && !train && !p.dbg_act;
   if (two_tile) NFB_CUDA(nfb::launch_render2(p, h->num_sms, st, &h->launches));
   else NFB_CUDA(nfb::launch_render(p, exact ? 1 : 0, h->num_sms, st, &h->launches));
   if (train) h->tr.valid = true;

@@ -128,22 +128,6 @@ constexpr ProgTable make_prog() {
 __constant__ ProgTable c_prog = make_prog();
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
-// Optional phase timers (NfbDebug.prof): cycles of one observer thread per role, summed over CTAs.
-struct PhaseTimer {
-  unsigned long long* dst;
-  long long t0;
-  __device__ __forceinline__ PhaseTimer(unsigned long long* d, bool on) : dst(on ? d : nullptr), t0(0) {
-    if (dst) t0 = clock64();
-  }
-  __device__ __forceinline__ void lap(int slot) {
-    if (dst) {
-      const long long t1 = clock64();
-      atomicAdd(dst + slot, (unsigned long long)(t1 - t0));
-      t0 = t1;
-    }
-  }
-};
-
 // Epilogue of one 64-column accumulator slice (this thread's share of one N-half): both TMEM loads in flight,
 // two independent bias/ReLU/convert chains, then the FP16 result overwrites the slice in place — hi in columns
 // [0,32), lo (exact mode) in [32,64).  All reads complete (wait::ld) before the first store.

@@ -107,6 +107,20 @@ __device__ __forceinline__ void epi_load64(uint32_t t_q, uint32_t bias, uint32_t
 #pragma unroll
   for (int j = 0; j < 16; ++j) { h[j] = ha[j]; h[16 + j] = hb[j]; }
 }
+// Same, with `keep` (the held half-0 result) stored to P while the accumulator loads are in flight.
+__device__ __forceinline__ void store32(uint32_t t_p, const uint32_t (&h)[32]);
+__device__ __forceinline__ void epi_store_load64(uint32_t t_keep, const uint32_t (&keep)[32], uint32_t t_q, uint32_t bias,
+                                                 uint32_t (&h)[32]) {
+  uint32_t va[32], vb[32], ha[16], hb[16], lo[16];
+  tmem_ld32(t_q, va);
+  tmem_ld32(t_q + 32, vb);
+  store32(t_keep, keep);
+  tmem_wait_ld();
+  epi_math<false>(va, bias, 0u, nullptr, ha, lo);
+  epi_math<false>(vb, bias + 128, 0u, nullptr, hb, lo);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { h[j] = ha[j]; h[16 + j] = hb[j]; }
+}
 __device__ __forceinline__ void store32(uint32_t t_p, const uint32_t (&h)[32]) {
   uint32_t a[16], b[16];
 #pragma unroll
@@ -162,9 +176,11 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
   if (warp == 0) {
     // ============================== weight producer ==============================
     uint32_t slot = 0, phase = 0, seq = 0;
+    PhaseTimer tm(p.prof, p.prof != nullptr && lane == 0);
     for (int it = 0; it < n_iter; ++it) {
       for (int t = 0; t < tiles_per_unit; ++t) {
         const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
+        tm.lap(41);
         for (int i = 0; i < kNumEntries; ++i) {
           const uint32_t w = c_prog.e[i].w;
           const uint32_t off = (w & 0xFFFFFu) << 4, bytes = (w >> 20) * 128u;
@@ -184,6 +200,8 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
     // ============================== MMA issuer ==============================
     uint32_t slot = 0, phase = 0;  // ring position at the start of the current group
     uint32_t ph_gate0 = 0, ph_gate1 = 0;
+    const bool prof_on = p.prof != nullptr;
+    long long acc_gate = 0, acc_full = 0, acc_issue = 0, tq = prof_on ? clock64() : 0;
     const uint64_t pe_desc0 = umma_smem_desc_sw128(smem_base + kOffPe);
     const uint64_t pe_desc1 = umma_smem_desc_sw128(smem_base + kOffPe + kTileM * 128);
     for (int it = 0; it < n_iter; ++it) {
@@ -194,17 +212,21 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
 #pragma unroll
           for (int x = 0; x < 2; ++x) {
             // stream x may run this half-step: its operand P_x is in place and its accumulator Q_x has been read
+            if (prof_on) { const long long tn = clock64(); acc_issue += tn - tq; tq = tn; }
             if (x == 0) { mbar_wait(bar_gate, ph_gate0); ph_gate0 ^= 1; }
             else        { mbar_wait(bar_gate + 8, ph_gate1); ph_gate1 ^= 1; }
             tc_fence_after_sync();
+            if (prof_on) { const long long tn = clock64(); acc_gate += tn - tq; tq = tn; }
             sl = slot; ph = phase;  // both streams walk the same ring slots
             const uint32_t p_tmem = tmem_base + (uint32_t)x * 256u;
             const uint32_t q_tmem = p_tmem + 128u;
             const uint64_t pe_desc = x ? pe_desc1 : pe_desc0;
             for (uint32_t j = 0; j < g_count; ++j) {
               const ProgEntry e = c_prog.e[g_first + j];
+              if (prof_on) { const long long tn = clock64(); acc_issue += tn - tq; tq = tn; }
               mbar_wait(bar_full + sl * 8, ph);  // stream Y finds the slot already filled
               tc_fence_after_sync();
+              if (prof_on) { const long long tn = clock64(); acc_full += tn - tq; tq = tn; }
               const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + sl * kSlotBytes);
               if (elect_one()) {
 #pragma unroll
@@ -224,6 +246,11 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
           slot = sl; phase = ph;
         }
       }
+    }
+    if (prof_on && lane == 0) {
+      atomicAdd(p.prof + 44, (unsigned long long)acc_issue);
+      atomicAdd(p.prof + 45, (unsigned long long)acc_gate);
+      atomicAdd(p.prof + 46, (unsigned long long)acc_full);
     }
   } else {
     // ============================== row warps ==============================
@@ -245,9 +272,11 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
     const int RR = 2 * R;            // rays per unit of work
     const bool has_bg = p.bg != nullptr;
     uint32_t ph_acc0 = 0, ph_acc1 = 0;
+    PhaseTimer tm(p.prof, p.prof != nullptr && etid == 0);
 
     for (int it = 0; it < n_iter; ++it) {
       const int unit = blockIdx.x + it * gridDim.x;
+      tm.lap(39);
       // ---- per-ray constants (ray slot qy = x * R + r)
       if (etid < RR) {
         RayP& rp = rayp[etid];
@@ -290,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
         rp.ped[6 * f + 3 + c] = rp.valid ? cs : 0.f;
       }
       named_bar_sync(kRowBarrier, kRowThreads);
+      tm.lap(0);
 
       for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1 && p.nf == 0) break;
@@ -375,6 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
         prologue(0, 0);
         prologue(1, 0);
         named_bar_sync(kRowBarrier, kRowThreads);  // carry_z of this pass is complete
+        tm.lap(2);
 
         for (int t = 0; t < n_tiles; ++t) {
           const int prow = t * 128 + row;
@@ -400,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
             }
             dirbias[ch * 128 + row] = acc0;
             dirbias[(ch + 2) * 128 + row] = acc1;
+            tm.lap(1);
           }
 
           uint32_t keep0[32], keep1[32];  // half-0 results of streams X / Y, held until P is dead
@@ -416,6 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                 if (x == 0) { mbar_wait(bar_accfull, ph_acc0); ph_acc0 ^= 1; }
                 else        { mbar_wait(bar_accfull + 8, ph_acc1); ph_acc1 ^= 1; }
                 tc_fence_after_sync();
+                tm.lap(10 + s);
                 uint32_t (&keep)[32] = x ? keep1 : keep0;
                 float& sigma_raw = x ? sigma_raw1 : sigma_raw0;
                 const RayP& rp = rayp[x * R + r];
@@ -424,8 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                     epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + c0), 0u, keep);
                   } else {       // P_x is dead: store half 0 (K atom ch), convert half 1 (K atom 2 + ch)
                     uint32_t hh[32];
-                    store32(t_p + 32 * ch, keep);
-                    epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + 128 + c0), 0u, hh);
+                    epi_store_load64(t_p + 32 * ch, keep, t_q + c0, smem_u32(bias_n + si.bias_off + 128 + c0), hh);
                     store32(t_p + 64 + 32 * ch, hh);
                     tmem_wait_st();
                   }
@@ -482,15 +514,18 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                   __syncwarp();
                   if (lane == 0) mbar_arrive(bar_gate + x * 8);
                 }
+                tm.lap(20 + s);
               }
             }
             if (s == 3 && t + 1 < n_tiles) {  // both PE buffers are free: encode the next tile pair under steps 4..9
               prologue(0, t + 1);
               prologue(1, t + 1);
+              tm.lap(2);
             }
           }
         }  // tile pairs
         named_bar_sync(kRowBarrier, kRowThreads);
+        tm.lap(3);
 
         // ---- debug dump of the sample depths
         {
@@ -521,8 +556,10 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
         }
         if (pass == 1 || p.nf == 0) {
           named_bar_sync(kRowBarrier, kRowThreads);  // carry buffers are reused by the next unit
+          tm.lap(4);
           continue;
         }
+        tm.lap(4);
 
         // ---- inverse-CDF resampling (nerf_helpers.py:344-387) on weights[1:-1] over the mid-point bins
         __syncwarp();
@@ -560,6 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
             }
         }
         named_bar_sync(kRowBarrier, kRowThreads);
+        tm.lap(5);
         // cat(z_coarse, z_samples) per ray into scr_sort (per stream: stride s_fine)
         const int SF = p.s_fine;
         for (int k = etid; k < RR * SF; k += kRowThreads) {
@@ -588,6 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
           scr_sort[x * kRowsMax + rr * SF + i] = val;
         }
         named_bar_sync(kRowBarrier, kRowThreads);
+        tm.lap(6);
         // ---- torch.sort(cat(z, z_samples)) (train_utils.py:126) as a rank merge (see nfb_render.cu)
         for (int k = etid; k < RR * SF; k += kRowThreads) {
           const int qy = k / SF, i = k - qy * SF;
@@ -615,6 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
           carry_z[x * kRowsMax + rr * SF + rank] = v;
         }
         named_bar_sync(kRowBarrier, kRowThreads);
+        tm.lap(7);
       }  // pass
     }    // units
     tc_fence_before_sync();

@@ -143,4 +143,21 @@ __device__ __forceinline__ float composite_ray(const float4* __restrict__ pre, c
 }
 
 
+// Optional phase timers (NfbDebug.prof): cycles of one observer thread per role, summed over CTAs.
+struct PhaseTimer {
+  unsigned long long* dst;
+  long long t0;
+  __device__ __forceinline__ PhaseTimer(unsigned long long* d, bool on) : dst(on ? d : nullptr), t0(0) {
+    if (dst) t0 = clock64();
+  }
+  __device__ __forceinline__ void lap(int slot) {
+    if (dst) {
+      const long long t1 = clock64();
+      atomicAdd(dst + slot, (unsigned long long)(t1 - t0));
+      t0 = t1;
+    }
+  }
+};
+
+
 }  // namespace nfb
