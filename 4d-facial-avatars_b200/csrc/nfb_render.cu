@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     {
       uint32_t slot = 0, phase = 0, ph_a0 = 0, ph_a1 = 0;
       PhaseTimer tm(p.prof, p.prof != nullptr && lane == 0);
-      const bool prof_on = p.prof != nullptr;
+      const bool prof_on = NFB_TIMERS && p.prof != nullptr;
       long long acc_gate = 0, acc_full = 0, acc_issue = 0, tq = prof_on ? clock64() : 0;
       const uint64_t pe_desc_hi = umma_smem_desc_sw128(smem_base + kOffPeHi);
       const uint64_t pe_desc_lo = umma_smem_desc_sw128(smem_base + kOffPeLo);

@@ -29,28 +29,35 @@
 namespace nfb {
 namespace v6 {
 
-constexpr int kNumSlots = 8;
+using Timer = PhaseTimer;
+
+constexpr int kNumSlots = 10;
 constexpr int kSlotBytes = 16384;
 constexpr int kRowsMax = 512;  // sample rows of one pass of one stream
 constexpr int kThreads = 320;  // producer warp + MMA warp + 8 row warps
-constexpr int kCluster = 2;
+#ifndef NFB_V6_CLUSTER
+#define NFB_V6_CLUSTER 2
+#endif
+constexpr int kCluster = NFB_V6_CLUSTER;  // CTAs sharing every weight half-unit through one multicast L2 read
 constexpr int kRowThreads = 256;
 constexpr uint32_t kRowBarrier = 1;
 
-// shared memory map
+// shared memory map.  The between-pass scratch (weights, cdf, bins, merge buffer) aliases the two positional-encoding
+// buffers: those are only read by the tensor core during a pass, the scratch only lives between passes.
 constexpr int kOffRing = 0;
 constexpr int kOffPe = kOffRing + kNumSlots * kSlotBytes;     // [2 streams][128 rows x 128 B]
-constexpr int kOffBias = kOffPe + 2 * kTileM * 128;
-constexpr int kOffRaw = kOffBias + 2 * kBiasFloats * 4;       // [2][kRowsMax] float4
-constexpr int kOffZ = kOffRaw + 2 * kRowsMax * 16;
-constexpr int kOffW = kOffZ + 2 * kRowsMax * 4;
+constexpr int kOffW = kOffPe;                                 // [2][kRowsMax] floats each, inside the PE buffers
 constexpr int kOffCdf = kOffW + 2 * kRowsMax * 4;
 constexpr int kOffBins = kOffCdf + 2 * kRowsMax * 4;
 constexpr int kOffSort = kOffBins + 2 * kRowsMax * 4;
-constexpr int kOffDirBias = kOffSort + 2 * kRowsMax * 4;      // [4 rays][128]
+static_assert(kOffSort + 2 * kRowsMax * 4 <= kOffPe + 2 * kTileM * 128, "scratch must fit in the PE buffers");
+constexpr int kOffBias = kOffPe + 2 * kTileM * 128;           // bias block of the CURRENT pass's network
+constexpr int kOffRaw = kOffBias + kBiasFloats * 4;           // [2][kRowsMax] float4
+constexpr int kOffZ = kOffRaw + 2 * kRowsMax * 16;
+constexpr int kOffDirBias = kOffZ + 2 * kRowsMax * 4;         // [4 rays][128]
 constexpr int kOffRay = kOffDirBias + 4 * 128 * 4;
 constexpr int kOffBars = kOffRay + 4 * kRayFloats * 4;
-constexpr int kNumBars = 2 * kNumSlots + 4;                   // full[8] empty[8] gate[2] accfull[2]
+constexpr int kNumBars = 2 * kNumSlots + 4;                   // full[] empty[] gate[2] accfull[2]
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0, "alignment");
@@ -107,20 +114,6 @@ __device__ __forceinline__ void epi_load64(uint32_t t_q, uint32_t bias, uint32_t
 #pragma unroll
   for (int j = 0; j < 16; ++j) { h[j] = ha[j]; h[16 + j] = hb[j]; }
 }
-// Same, with `keep` (the held half-0 result) stored to P while the accumulator loads are in flight.
-__device__ __forceinline__ void store32(uint32_t t_p, const uint32_t (&h)[32]);
-__device__ __forceinline__ void epi_store_load64(uint32_t t_keep, const uint32_t (&keep)[32], uint32_t t_q, uint32_t bias,
-                                                 uint32_t (&h)[32]) {
-  uint32_t va[32], vb[32], ha[16], hb[16], lo[16];
-  tmem_ld32(t_q, va);
-  tmem_ld32(t_q + 32, vb);
-  store32(t_keep, keep);
-  tmem_wait_ld();
-  epi_math<false>(va, bias, 0u, nullptr, ha, lo);
-  epi_math<false>(vb, bias + 128, 0u, nullptr, hb, lo);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) { h[j] = ha[j]; h[16 + j] = hb[j]; }
-}
 __device__ __forceinline__ void store32(uint32_t t_p, const uint32_t (&h)[32]) {
   uint32_t a[16], b[16];
 #pragma unroll
@@ -157,10 +150,6 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
     tmem_alloc(smem_base + kOffTmemPtr, 512);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < kBiasFloats; i += kThreads) {
-    bias_s[i] = p.bias[0][i];
-    bias_s[kBiasFloats + i] = (p.nf > 0) ? p.bias[1][i] : 0.f;
-  }
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();
@@ -176,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
   if (warp == 0) {
     // ============================== weight producer ==============================
     uint32_t slot = 0, phase = 0, seq = 0;
-    PhaseTimer tm(p.prof, p.prof != nullptr && lane == 0);
+    Timer tm(p.prof, p.prof != nullptr && lane == 0);
     for (int it = 0; it < n_iter; ++it) {
       for (int t = 0; t < tiles_per_unit; ++t) {
         const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
@@ -200,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
     // ============================== MMA issuer ==============================
     uint32_t slot = 0, phase = 0;  // ring position at the start of the current group
     uint32_t ph_gate0 = 0, ph_gate1 = 0;
-    const bool prof_on = p.prof != nullptr;
+    const bool prof_on = NFB_TIMERS && p.prof != nullptr;
     long long acc_gate = 0, acc_full = 0, acc_issue = 0, tq = prof_on ? clock64() : 0;
     const uint64_t pe_desc0 = umma_smem_desc_sw128(smem_base + kOffPe);
     const uint64_t pe_desc1 = umma_smem_desc_sw128(smem_base + kOffPe + kTileM * 128);
@@ -224,8 +213,10 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
             for (uint32_t j = 0; j < g_count; ++j) {
               const ProgEntry e = c_prog.e[g_first + j];
               if (prof_on) { const long long tn = clock64(); acc_issue += tn - tq; tq = tn; }
-              mbar_wait(bar_full + sl * 8, ph);  // stream Y finds the slot already filled
-              tc_fence_after_sync();
+              if (x == 0) {  // stream Y reuses the slots stream X has just waited for
+                mbar_wait(bar_full + sl * 8, ph);
+                tc_fence_after_sync();
+              }
               if (prof_on) { const long long tn = clock64(); acc_full += tn - tq; tq = tn; }
               const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + sl * kSlotBytes);
               if (elect_one()) {
@@ -272,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
     const int RR = 2 * R;            // rays per unit of work
     const bool has_bg = p.bg != nullptr;
     uint32_t ph_acc0 = 0, ph_acc1 = 0;
-    PhaseTimer tm(p.prof, p.prof != nullptr && etid == 0);
+    Timer tm(p.prof, p.prof != nullptr && etid == 0);
 
     for (int it = 0; it < n_iter; ++it) {
       const int unit = blockIdx.x + it * gridDim.x;
@@ -326,7 +317,9 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
         const int S = pass ? p.s_fine : p.nc;
         const int rows = R * S;  // rows of one stream in this pass
         const int n_tiles = pass ? p.tiles_f : p.tiles_c;
-        const float* bias_n = bias_s + pass * kBiasFloats;
+        const float* bias_n = bias_s;
+        if (p.nf > 0 || it == 0)  // bias block of this pass's network (published by the barrier after the first prologue)
+          for (int k = etid; k < kBiasFloats; k += kRowThreads) bias_s[k] = p.bias[pass][k];
 
         // ---- sample depth + positional encoding of tile t of stream x -> PE buffer x
         auto prologue = [&](int x, int t) {
@@ -457,7 +450,8 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                     epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + c0), 0u, keep);
                   } else {       // P_x is dead: store half 0 (K atom ch), convert half 1 (K atom 2 + ch)
                     uint32_t hh[32];
-                    epi_store_load64(t_p + 32 * ch, keep, t_q + c0, smem_u32(bias_n + si.bias_off + 128 + c0), hh);
+                    store32(t_p + 32 * ch, keep);
+                    epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + 128 + c0), 0u, hh);
                     store32(t_p + 64 + 32 * ch, hh);
                     tmem_wait_st();
                   }
