@@ -42,6 +42,14 @@ __device__ __forceinline__ void pe_sincos(float y, float& s, float& c) {
   }
 }
 
+// (a0, a1) += (b0, b1) as one packed FP32 add (sm_100 FADD2; round-to-nearest per element, like two scalar adds).
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 rc, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+
 // ------------------------------------------------------------------------------------------------
 // Epilogue math of one 32-column accumulator chunk: x = acc + bias (+ extra); ReLU; FP16 hi (and lo).
 template <bool EXACT>
@@ -49,16 +57,19 @@ __device__ __forceinline__ void epi_math(const uint32_t (&v)[32], uint32_t bias,
                                          float* __restrict__ dump, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
   float x[32];  // bias / extra are shared-memory byte addresses (extra == 0: none)
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
+  for (int j = 0; j < 32; j += 4) {  // packed FP32 adds (FADD2): same rounding as scalar adds, half the issue slots
     const float4 b = lds128(bias + j * 4);
-    x[j] = __uint_as_float(v[j]) + b.x; x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
-    x[j + 2] = __uint_as_float(v[j + 2]) + b.z; x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+    x[j] = __uint_as_float(v[j]); x[j + 1] = __uint_as_float(v[j + 1]);
+    x[j + 2] = __uint_as_float(v[j + 2]); x[j + 3] = __uint_as_float(v[j + 3]);
+    add_f32x2(x[j], x[j + 1], b.x, b.y);
+    add_f32x2(x[j + 2], x[j + 3], b.z, b.w);
   }
   if (extra) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 e = lds128(extra + j * 4);
-      x[j] += e.x; x[j + 1] += e.y; x[j + 2] += e.z; x[j + 3] += e.w;
+      add_f32x2(x[j], x[j + 1], e.x, e.y);
+      add_f32x2(x[j + 2], x[j + 3], e.z, e.w);
     }
   }
   if (dump) {
