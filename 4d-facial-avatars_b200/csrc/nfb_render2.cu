@@ -114,12 +114,111 @@ __device__ __forceinline__ void epi_load64(uint32_t t_q, uint32_t bias, uint32_t
 #pragma unroll
   for (int j = 0; j < 16; ++j) { h[j] = ha[j]; h[16 + j] = hb[j]; }
 }
+// Half-0 variant: the result stays in registers, so the accumulator is free as soon as it has been LOADED — the gate
+// (`bar`, one arrival per warp) is signalled before the arithmetic, which then overlaps the next half-step's MMAs.
+__device__ __forceinline__ void epi_load64_early(uint32_t t_q, uint32_t bias, uint32_t extra, uint32_t (&h)[32], uint32_t bar, int lane) {
+  uint32_t va[32], vb[32], ha[16], hb[16], lo[16];
+  tmem_ld32(t_q, va);
+  tmem_ld32(t_q + 32, vb);
+  tmem_wait_ld();
+  tc_fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+  epi_math<false>(va, bias, extra, nullptr, ha, lo);
+  epi_math<false>(vb, bias + 128, extra ? extra + 128 : 0u, nullptr, hb, lo);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { h[j] = ha[j]; h[16 + j] = hb[j]; }
+}
 __device__ __forceinline__ void store32(uint32_t t_p, const uint32_t (&h)[32]) {
   uint32_t a[16], b[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) { a[j] = h[j]; b[j] = h[16 + j]; }
   tmem_st16(t_p, a);
   tmem_st16(t_p + 16, b);
+}
+
+#ifndef NFB_V6_PROLOGUE_NOINLINE
+#define NFB_V6_PROLOGUE_NOINLINE 0
+#endif
+#if NFB_V6_PROLOGUE_NOINLINE
+#define NFB_V6_PROLOGUE_ATTR __noinline__
+#else
+#define NFB_V6_PROLOGUE_ATTR __forceinline__
+#endif
+// Sample depth + positional encoding of tile t of stream x -> PE buffer x (63 lanes + zero pad, FP16, swizzled).
+__device__ NFB_V6_PROLOGUE_ATTR void prologue_fn(const RenderParams& p, const RayP* __restrict__ rayp, float* __restrict__ carry_z,
+                                                 uint8_t* __restrict__ pe_base, int x, int t, int pass, int S, int rows, int R,
+                                                 int row, int ch) {
+    const int prow = t * 128 + row;
+    const bool live = prow < rows;
+    const int r = live ? prow / S : 0;
+    const int i = live ? prow - r * S : 0;
+    const RayP& rp = rayp[x * R + r];
+    float z = 0.f;
+    if (live) {
+      if (pass == 0) {
+        const float tc = p.t_coarse[i];
+        z = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tc)), __fmul_rn(p.far_, tc));
+        if (p.perturb) {  // stratified jitter (train_utils.py:69-76)
+          float lower = z, upper = z;
+          if (i > 0) {
+            const float tp = p.t_coarse[i - 1];
+            const float zp = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tp)), __fmul_rn(p.far_, tp));
+            lower = __fmul_rn(0.5f, __fadd_rn(z, zp));
+          }
+          if (i < S - 1) {
+            const float tn = p.t_coarse[i + 1];
+            const float zn = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tn)), __fmul_rn(p.far_, tn));
+            upper = __fmul_rn(0.5f, __fadd_rn(zn, z));
+          }
+          const float tr = rp.valid ? p.t_rand[(size_t)rp.gidx * p.nc + i] : 0.f;
+          z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
+        }
+        if (ch == 0) carry_z[x * kRowsMax + prow] = z;
+      } else {
+        z = carry_z[x * kRowsMax + prow];
+      }
+    }
+    const float px = __fadd_rn(rp.o[0], __fmul_rn(rp.d[0], z));
+    const float py = __fadd_rn(rp.o[1], __fmul_rn(rp.d[1], z));
+    const float pz = __fadd_rn(rp.o[2], __fmul_rn(rp.d[2], z));
+    float f[32];
+    if (ch == 0) {  // lanes 0..31: xyz, frequencies 0..3, sin of frequency 4, cos(x), cos(y) of frequency 4
+      f[0] = px; f[1] = py; f[2] = pz;
+#pragma unroll
+      for (int fr = 0; fr < 4; ++fr) {
+        const float sc = (float)(1 << fr);
+        pe_sincos<false>(px * sc, f[3 + 6 * fr + 0], f[3 + 6 * fr + 3]);
+        pe_sincos<false>(py * sc, f[3 + 6 * fr + 1], f[3 + 6 * fr + 4]);
+        pe_sincos<false>(pz * sc, f[3 + 6 * fr + 2], f[3 + 6 * fr + 5]);
+      }
+      float cz;
+      pe_sincos<false>(px * 16.f, f[27], f[30]);
+      pe_sincos<false>(py * 16.f, f[28], f[31]);
+      pe_sincos<false>(pz * 16.f, f[29], cz);
+    } else {        // lanes 32..63: cos(z) of frequency 4, frequencies 5..9, zero pad
+      float sz;
+      pe_sincos<false>(pz * 16.f, sz, f[0]);
+#pragma unroll
+      for (int fr = 5; fr < 10; ++fr) {
+        const float sc = (float)(1 << fr);
+        const int b = 6 * fr - 29;
+        pe_sincos<false>(px * sc, f[b + 0], f[b + 3]);
+        pe_sincos<false>(py * sc, f[b + 1], f[b + 4]);
+        pe_sincos<false>(pz * sc, f[b + 2], f[b + 5]);
+      }
+      f[31] = 0.f;
+    }
+    uint8_t* pe = pe_base + x * (kTileM * 128);
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      uint32_t hi[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hi[e] = pack_f16x2(f[qq * 8 + 2 * e], f[qq * 8 + 2 * e + 1]);
+      const int off = row * 128 + (((ch * 4 + qq) ^ (row & 7)) << 4);
+      *reinterpret_cast<uint4*>(pe + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    }
+    fence_proxy_async_smem();
 }
 
 __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_constant__ RenderParams p) {
@@ -210,27 +309,44 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
             const uint32_t p_tmem = tmem_base + (uint32_t)x * 256u;
             const uint32_t q_tmem = p_tmem + 128u;
             const uint64_t pe_desc = x ? pe_desc1 : pe_desc0;
-            for (uint32_t j = 0; j < g_count; ++j) {
-              const ProgEntry e = c_prog.e[g_first + j];
-              if (prof_on) { const long long tn = clock64(); acc_issue += tn - tq; tq = tn; }
+            // Two weight units (8 MMAs) per elected block.  At N = 128 an MMA is short (about 75 cycles), so per-unit
+            // waits / elect / warp syncs bound the issue rate (tools/mma_mix.cu: 106 cycles per MMA with 4 per block, 78 with
+            // 8; worse while the row warps are busy): 2 units per block measured 4.38 M rays/s against 3.96 M with 1.  More
+            // per block is slower again (4 units: 3.54 M, whole group: 3.99 M) because the block then waits for all of its
+            // weight slots before the first MMA — the weights arrive just in time.  Everything the MMAs consume is computed
+            // outside the elected block so it stays in uniform registers.
+            for (uint32_t j = 0; j < g_count; j += 2) {
+              const bool two = j + 1 < g_count;
+              const ProgEntry e0 = c_prog.e[g_first + j];
+              const ProgEntry e1 = c_prog.e[g_first + (two ? j + 1 : j)];
+              uint32_t sl1 = sl + 1, ph1 = ph;
+              if (sl1 == kNumSlots) { sl1 = 0; ph1 ^= 1; }
               if (x == 0) {  // stream Y reuses the slots stream X has just waited for
                 mbar_wait(bar_full + sl * 8, ph);
+                if (two) mbar_wait(bar_full + sl1 * 8, ph1);
                 tc_fence_after_sync();
               }
-              if (prof_on) { const long long tn = clock64(); acc_full += tn - tq; tq = tn; }
-              const uint64_t b_desc = umma_smem_desc_sw128(smem_base + kOffRing + sl * kSlotBytes);
+              const uint64_t b_desc0 = umma_smem_desc_sw128(smem_base + kOffRing + sl * kSlotBytes);
+              const uint64_t b_desc1 = umma_smem_desc_sw128(smem_base + kOffRing + sl1 * kSlotBytes);
               if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t bd = b_desc + (uint64_t)(ks * 2);
-                  const uint32_t acc_flag = ((e.z & kFirst) && ks == 0) ? 0u : 1u;
-                  if (e.z & kFromPe) umma_ss(q_tmem, pe_desc + (uint64_t)(ks * 2), bd, e.x, acc_flag);
-                  else umma_ts(q_tmem, p_tmem + e.y + ks * 8, bd, e.x, acc_flag);
+                  const uint64_t bd = b_desc0 + (uint64_t)(ks * 2);
+                  const uint32_t acc_flag = ((e0.z & kFirst) && ks == 0) ? 0u : 1u;
+                  if (e0.z & kFromPe) umma_ss(q_tmem, pe_desc + (uint64_t)(ks * 2), bd, e0.x, acc_flag);
+                  else umma_ts(q_tmem, p_tmem + e0.y + ks * 8, bd, e0.x, acc_flag);
                 }
                 if (x == 1) umma_commit_multicast(bar_empty + sl * 8, kAllCtas);  // both streams are done with the slot
-                if (e.z & kLast) umma_commit(bar_accfull + x * 8);
+                if (two) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_ts(q_tmem, p_tmem + e1.y + ks * 8, b_desc1 + (uint64_t)(ks * 2), e1.x, 1u);  // never the PE atom, never first
+                  if (x == 1) umma_commit_multicast(bar_empty + sl1 * 8, kAllCtas);
+                }
+                if ((two ? e1.z : e0.z) & kLast) umma_commit(bar_accfull + x * 8);
               }
               __syncwarp();
+              if (two) { sl = sl1; ph = ph1; }
               if (++sl == kNumSlots) { sl = 0; ph ^= 1; }
             }
           }
@@ -321,79 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
         if (p.nf > 0 || it == 0)  // bias block of this pass's network (published by the barrier after the first prologue)
           for (int k = etid; k < kBiasFloats; k += kRowThreads) bias_s[k] = p.bias[pass][k];
 
-        // ---- sample depth + positional encoding of tile t of stream x -> PE buffer x
-        auto prologue = [&](int x, int t) {
-          const int prow = t * 128 + row;
-          const bool live = prow < rows;
-          const int r = live ? prow / S : 0;
-          const int i = live ? prow - r * S : 0;
-          const RayP& rp = rayp[x * R + r];
-          float z = 0.f;
-          if (live) {
-            if (pass == 0) {
-              const float tc = p.t_coarse[i];
-              z = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tc)), __fmul_rn(p.far_, tc));
-              if (p.perturb) {  // stratified jitter (train_utils.py:69-76)
-                float lower = z, upper = z;
-                if (i > 0) {
-                  const float tp = p.t_coarse[i - 1];
-                  const float zp = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tp)), __fmul_rn(p.far_, tp));
-                  lower = __fmul_rn(0.5f, __fadd_rn(z, zp));
-                }
-                if (i < S - 1) {
-                  const float tn = p.t_coarse[i + 1];
-                  const float zn = __fadd_rn(__fmul_rn(p.near_, __fsub_rn(1.f, tn)), __fmul_rn(p.far_, tn));
-                  upper = __fmul_rn(0.5f, __fadd_rn(zn, z));
-                }
-                const float tr = rp.valid ? p.t_rand[(size_t)rp.gidx * p.nc + i] : 0.f;
-                z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
-              }
-              if (ch == 0) carry_z[x * kRowsMax + prow] = z;
-            } else {
-              z = carry_z[x * kRowsMax + prow];
-            }
-          }
-          const float px = __fadd_rn(rp.o[0], __fmul_rn(rp.d[0], z));
-          const float py = __fadd_rn(rp.o[1], __fmul_rn(rp.d[1], z));
-          const float pz = __fadd_rn(rp.o[2], __fmul_rn(rp.d[2], z));
-          float f[32];
-          if (ch == 0) {  // lanes 0..31: xyz, frequencies 0..3, sin of frequency 4, cos(x), cos(y) of frequency 4
-            f[0] = px; f[1] = py; f[2] = pz;
-#pragma unroll
-            for (int fr = 0; fr < 4; ++fr) {
-              const float sc = (float)(1 << fr);
-              pe_sincos<false>(px * sc, f[3 + 6 * fr + 0], f[3 + 6 * fr + 3]);
-              pe_sincos<false>(py * sc, f[3 + 6 * fr + 1], f[3 + 6 * fr + 4]);
-              pe_sincos<false>(pz * sc, f[3 + 6 * fr + 2], f[3 + 6 * fr + 5]);
-            }
-            float cz;
-            pe_sincos<false>(px * 16.f, f[27], f[30]);
-            pe_sincos<false>(py * 16.f, f[28], f[31]);
-            pe_sincos<false>(pz * 16.f, f[29], cz);
-          } else {        // lanes 32..63: cos(z) of frequency 4, frequencies 5..9, zero pad
-            float sz;
-            pe_sincos<false>(pz * 16.f, sz, f[0]);
-#pragma unroll
-            for (int fr = 5; fr < 10; ++fr) {
-              const float sc = (float)(1 << fr);
-              const int b = 6 * fr - 29;
-              pe_sincos<false>(px * sc, f[b + 0], f[b + 3]);
-              pe_sincos<false>(py * sc, f[b + 1], f[b + 4]);
-              pe_sincos<false>(pz * sc, f[b + 2], f[b + 5]);
-            }
-            f[31] = 0.f;
-          }
-          uint8_t* pe = smem + kOffPe + x * (kTileM * 128);
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            uint32_t hi[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) hi[e] = pack_f16x2(f[qq * 8 + 2 * e], f[qq * 8 + 2 * e + 1]);
-            const int off = row * 128 + (((ch * 4 + qq) ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(pe + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          }
-          fence_proxy_async_smem();
-        };
+        auto prologue = [&](int x, int t) { prologue_fn(p, rayp, carry_z, smem + kOffPe, x, t, pass, S, rows, R, row, ch); };
 
         prologue(0, 0);
         prologue(1, 0);
@@ -443,11 +487,13 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                 tc_fence_after_sync();
                 tm.lap(10 + s);
                 uint32_t (&keep)[32] = x ? keep1 : keep0;
+                bool arrived = false;
                 float& sigma_raw = x ? sigma_raw1 : sigma_raw0;
                 const RayP& rp = rayp[x * R + r];
                 if (s <= 5) {
-                  if (h == 0) {  // outputs [64 ch, +64) of features 0..127 -> registers
-                    epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + c0), 0u, keep);
+                  if (h == 0) {  // outputs [64 ch, +64) of features 0..127 -> registers (gate signalled inside)
+                    epi_load64_early(t_q + c0, smem_u32(bias_n + si.bias_off + c0), 0u, keep, bar_gate + x * 8, lane);
+                    arrived = true;
                   } else {       // P_x is dead: store half 0 (K atom ch), convert half 1 (K atom 2 + ch)
                     uint32_t hh[32];
                     store32(t_p + 32 * ch, keep);
@@ -457,7 +503,9 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                   }
                 } else if (s == 6) {
                   if (h == 0) {
-                    epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + c0), smem_u32(dirbias + (x * R + r) * 128 + c0), keep);
+                    epi_load64_early(t_q + c0, smem_u32(bias_n + si.bias_off + c0), smem_u32(dirbias + (x * R + r) * 128 + c0), keep,
+                                     bar_gate + x * 8, lane);
+                    arrived = true;
                   } else {  // sigma = column 0 of the 16-wide second half; then g0 becomes the operand (K = 128)
                     if (ch == 0) {
                       uint32_t v[4];
@@ -503,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                     carry_raw[x * kRowsMax + prow] = pre;
                   }
                 }
-                if (s < kNumSteps - 1) {  // Q_x has been read (and, after a step's last half, P_x holds the next operand)
+                if (s < kNumSteps - 1 && !arrived) {  // Q_x has been read (and, after a step's last half, P_x holds the next operand)
                   tc_fence_before_sync();
                   __syncwarp();
                   if (lane == 0) mbar_arrive(bar_gate + x * 8);
