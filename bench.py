@@ -12,7 +12,7 @@ Synthetic per-frame pose / expression / latent / background and random-init weig
            when N>1), timed with CUDA events per step (L2 flushed between steps, outside the events).
 `e2e`    : the same frame through the C-ABI host entry nfb_render_frame_host: pinned host expression / latent /
            background in, 11 floats per ray out, copies inside the timed region.
-`roofline`: dominant kernel = render_kernel; achieved = algorithmic FLOP per launch (1,100,032 FLOP per MLP
+`roofline`: dominant kernel = the render kernel (fast mode: nfb::v6::render2_kernel, two tiles in flight); achieved = algorithmic FLOP per launch (1,100,032 FLOP per MLP
            evaluation x (2*Nc+Nf) evaluations per ray x rays) / its CUDA-event time; peak from MEASURED_PEAKS.json.
 `cpu_baseline`: the oracle (a port of the reference, oracle/nerface_oracle.py) on the host cores for a 64x64 crop.
 """
@@ -267,7 +267,9 @@ def main():
         achieved = flop_per_launch / (k_ms * 1e-3) / 1e12
         peak = pk["bf16_tflops"]
         traffic = None  # dram bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
-        tpath = os.path.join(ROOT, "profiles", "r1_render_kernel_ncu.json")
+        two_tile = a.precision == "fast" and os.environ.get("NFB_KERNEL") != "v4"
+        kernel_name = "nfb::v6::render2_kernel" if two_tile else "nfb::render_kernel"
+        tpath = os.path.join(ROOT, "profiles", "r1b_render_kernel_ncu.json" if two_tile else "r1_render_kernel_ncu.json")
         if os.path.exists(tpath) and (H, W, nc, nf, a.precision) == (512, 512, 64, 128, "fast"):
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
@@ -319,8 +321,8 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "frac_of_sustained": achieved / pk.get("bf16_tflops_sustained", peak), "peak_source": pk_src,
-                         "kernel": "nfb::render_kernel", "kernel_ms": k_ms, "flop_per_launch": flop_per_launch, "traffic": traffic,
-                         "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/r1_render_kernel_ncu.md)"},
+                         "kernel": kernel_name, "kernel_ms": k_ms, "flop_per_launch": flop_per_launch, "traffic": traffic,
+                         "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, profiles/" + os.path.basename(tpath).replace(".json", ".md") + ")"},
             "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
