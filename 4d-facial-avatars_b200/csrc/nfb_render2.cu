@@ -34,7 +34,17 @@ using Timer = PhaseTimer;
 constexpr int kNumSlots = 10;
 constexpr int kSlotBytes = 16384;
 constexpr int kRowsMax = 512;  // sample rows of one pass of one stream
-constexpr int kThreads = 320;  // producer warp + MMA warp + 8 row warps
+#ifndef NFB_V6_ISSUE
+#define NFB_V6_ISSUE 2   // weight units per elected MMA block (1 or 2)
+#endif
+#ifndef NFB_V6_DUAL
+#define NFB_V6_DUAL 1
+#endif
+// NFB_V6_DUAL=1 (default; measured 4.51 M rays/s against 4.37 M): one MMA-issuing warp per stream (warps 1 and 2, on different SM sub-partitions) instead of one warp
+// issuing both streams' groups in turn; the row warps then start at warp 4 (warp 3 idles) and every ring slot is released
+// by two commits per CTA.
+constexpr int kRowWarp0 = NFB_V6_DUAL ? 4 : 2;
+constexpr int kThreads = (kRowWarp0 + 8) * 32;  // producer warp + MMA warp(s) + 8 row warps
 #ifndef NFB_V6_CLUSTER
 #define NFB_V6_CLUSTER 2
 #endif
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumSlots; ++i) {
       mbar_init(bar_full + i * 8, 1);
-      mbar_init(bar_empty + i * 8, kCluster);
+      mbar_init(bar_empty + i * 8, (NFB_V6_DUAL ? 2 : 1) * kCluster);
     }
     for (int x = 0; x < 2; ++x) {
       mbar_init(bar_gate + x * 8, kRowThreads / 32);
@@ -284,6 +294,57 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
         }
       }
     }
+#if NFB_V6_DUAL
+  } else if (warp == 1 || warp == 2) {
+    // ============================== MMA issuer of stream x = warp - 1 ==============================
+    const int x = warp - 1;
+    uint32_t sl = 0, ph = 0, ph_gate = 0;
+    const uint32_t p_tmem = tmem_base + (uint32_t)x * 256u;
+    const uint32_t q_tmem = p_tmem + 128u;
+    const uint64_t pe_desc = umma_smem_desc_sw128(smem_base + kOffPe + x * (kTileM * 128));
+    for (int it = 0; it < n_iter; ++it) {
+      for (int t = 0; t < tiles_per_unit; ++t) {
+        for (int g = 0; g < kNumGroups; ++g) {
+          const uint32_t g_first = c_prog.g[g].first, g_count = c_prog.g[g].count;
+          mbar_wait(bar_gate + x * 8, ph_gate);  // operand P_x in place, accumulator Q_x read
+          ph_gate ^= 1;
+          tc_fence_after_sync();
+          for (uint32_t j = 0; j < g_count; j += NFB_V6_ISSUE) {
+            const bool two = (NFB_V6_ISSUE == 2) && j + 1 < g_count;
+            const ProgEntry e0 = c_prog.e[g_first + j];
+            const ProgEntry e1 = c_prog.e[g_first + (two ? j + 1 : j)];
+            uint32_t sl1 = sl + 1, ph1 = ph;
+            if (sl1 == kNumSlots) { sl1 = 0; ph1 ^= 1; }
+            mbar_wait(bar_full + sl * 8, ph);
+            if (two) mbar_wait(bar_full + sl1 * 8, ph1);
+            tc_fence_after_sync();
+            const uint64_t b_desc0 = umma_smem_desc_sw128(smem_base + kOffRing + sl * kSlotBytes);
+            const uint64_t b_desc1 = umma_smem_desc_sw128(smem_base + kOffRing + sl1 * kSlotBytes);
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t bd = b_desc0 + (uint64_t)(ks * 2);
+                const uint32_t acc_flag = ((e0.z & kFirst) && ks == 0) ? 0u : 1u;
+                if (e0.z & kFromPe) umma_ss(q_tmem, pe_desc + (uint64_t)(ks * 2), bd, e0.x, acc_flag);
+                else umma_ts(q_tmem, p_tmem + e0.y + ks * 8, bd, e0.x, acc_flag);
+              }
+              umma_commit_multicast(bar_empty + sl * 8, kAllCtas);  // this stream is done with the slot
+              if (two) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_ts(q_tmem, p_tmem + e1.y + ks * 8, b_desc1 + (uint64_t)(ks * 2), e1.x, 1u);
+                umma_commit_multicast(bar_empty + sl1 * 8, kAllCtas);
+              }
+              if ((two ? e1.z : e0.z) & kLast) umma_commit(bar_accfull + x * 8);
+            }
+            __syncwarp();
+            if (two) { sl = sl1; ph = ph1; }
+            if (++sl == kNumSlots) { sl = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+#else
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     uint32_t slot = 0, phase = 0;  // ring position at the start of the current group
@@ -359,12 +420,13 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
       atomicAdd(p.prof + 45, (unsigned long long)acc_gate);
       atomicAdd(p.prof + 46, (unsigned long long)acc_full);
     }
-  } else {
+#endif
+  } else if (warp >= kRowWarp0) {
     // ============================== row warps ==============================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int ch = (warp - 2) >> 2;
-    const int ew = warp - 2;
+    const int ch = (warp - kRowWarp0) >> 2;
+    const int ew = warp - kRowWarp0;
     const int etid = ch * 128 + row;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float4* carry_raw = reinterpret_cast<float4*>(smem + kOffRaw);  // [x * kRowsMax + prow]
