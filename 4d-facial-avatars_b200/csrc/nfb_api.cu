@@ -412,6 +412,17 @@ int nfb_render_frame_host(NfbHandle* h, const float pose[12], const double intri
   return NFB_OK;
 }
 
+int nfb_debug_schedule(int which, int index, uint32_t* out, int out_words) {
+  if (index >= 0 && (!out || out_words < 10)) return -1;
+  switch (which) {
+    case 0: return nfb::debug_prog_v4(index, out);
+    case 1: return nfb::debug_prog_v6(index, out);
+    case 2: return nfb::debug_prog_chain(index, out);
+    case 3: return nfb::debug_jobs_dw(index, out);
+    default: return -1;
+  }
+}
+
 int nfb_launch_count(NfbHandle* h, long long* out) {
   if (!h || !out) return NFB_ERR_INVALID;
   *out = h->launches;

@@ -83,6 +83,11 @@ struct DwParams {
   float* acc;
   const float* scal;
 };
+// host copies of the compile-time schedules (nfb_debug_schedule); index < 0: number of entries; else words written or -1
+int debug_prog_v4(int index, uint32_t* out);
+int debug_prog_v6(int index, uint32_t* out);
+int debug_prog_chain(int index, uint32_t* out);
+int debug_jobs_dw(int index, uint32_t* out);
 cudaError_t train_kernels_setup();
 cudaError_t launch_pack_bwd(NetBuffers& nb, const float* const params[26], cudaStream_t st, long long* launches);
 cudaError_t launch_cond(const float* expr, const float* latent, float* cond, cudaStream_t st, long long* launches);

@@ -788,6 +788,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
   }
 }
 
+int debug_prog_v4(int index, uint32_t* out) {  // host copy of the per-tile unit program (tests)
+  constexpr ProgTable t = make_prog();
+  if (index < 0) return kTileUnits;
+  if (index >= kTileUnits) return -1;
+  out[0] = t.e[index].x; out[1] = t.e[index].y; out[2] = t.e[index].z; out[3] = t.e[index].w;
+  return 4;
+}
+
 cudaError_t render_kernel_setup() {
   cudaError_t e = cudaFuncSetAttribute(render_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;

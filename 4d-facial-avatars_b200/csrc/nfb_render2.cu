@@ -774,6 +774,17 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
 
 }  // namespace v6
 
+int debug_prog_v6(int index, uint32_t* out) {  // host copy of the half-step program (tests): 4 words + group index
+  if (index < 0) return v6::kNumEntries;
+  if (index >= v6::kNumEntries) return -1;
+  const v6::ProgEntry& e = v6::kProgHost.e[index];
+  out[0] = e.x; out[1] = e.y; out[2] = e.z; out[3] = e.w;
+  int g = 0;
+  while (g + 1 < v6::kNumGroups && (int)v6::kProgHost.g[g + 1].first <= index) ++g;
+  out[4] = (uint32_t)g;
+  return 5;
+}
+
 cudaError_t render2_kernel_setup() {
   return cudaFuncSetAttribute(v6::render2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v6::kSmemBytes);
 }

@@ -814,6 +814,26 @@ __global__ void cond_kernel(const float* __restrict__ expr, const float* __restr
 // ================================================================================================
 // host-side launchers
 // ================================================================================================
+int debug_prog_chain(int index, uint32_t* out) {
+  constexpr chain::ProgTable t = chain::make_prog();
+  if (index < 0) return chain::kTileUnits;
+  if (index >= chain::kTileUnits) return -1;
+  out[0] = t.e[index].x; out[1] = t.e[index].y; out[2] = t.e[index].z; out[3] = t.e[index].w;
+  return 4;
+}
+int debug_jobs_dw(int index, uint32_t* out) {
+  constexpr dw::JobTable t = dw::make_jobs();
+  if (index < 0) return dw::kNumJobs;
+  if (index >= dw::kNumJobs) return -1;
+  const dw::Job& j = t.j[index];
+  const int v[9] = {j.a_off, j.a_rows, j.a_half, j.b_off, j.b_rows, j.bias_layer, j.out_off, j.out_ld, j.out_row0};
+  for (int i = 0; i < 9; ++i) out[i] = (uint32_t)v[i];
+  int g = 0;
+  while (g + 1 < dw::kGroups && t.group_begin[g + 1] <= index) ++g;
+  out[9] = (uint32_t)g;
+  return 10;
+}
+
 cudaError_t train_kernels_setup() {
   cudaError_t e = cudaFuncSetAttribute(chain::chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::kSmemBytes);
   if (e != cudaSuccess) return e;

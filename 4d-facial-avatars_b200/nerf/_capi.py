@@ -12,7 +12,7 @@ NFB_PREC_FAST, NFB_PREC_EXACT = 0, 1
 
 EXPORTS = ["nfb_version", "nfb_strerror", "nfb_last_cuda_error", "nfb_create", "nfb_destroy", "nfb_load_weights",
            "nfb_set_frame", "nfb_render_forward", "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace",
-           "nfb_render_forward_train", "nfb_render_backward", "nfb_train_debug"]
+           "nfb_render_forward_train", "nfb_render_backward", "nfb_train_debug", "nfb_debug_schedule"]
 
 
 class NfbModelDims(C.Structure):

@@ -212,6 +212,13 @@ int nfb_render_frame_host(NfbHandle* h, const float pose[12], const double intri
                           const float* background_host /* [rows*width,3] or NULL */,
                           const NfbSampling* sampling, float* out_host, void* stream);
 
+/* Test hook, host only (no CUDA call): the compile-time schedules the kernels execute.  which: 0 = one-tile render program,
+ * 1 = two-tile render program (word 4 = half-step group), 2 = backward chain program (each: idesc, TMEM columns, flags,
+ * (stream offset / 16) | rows << 20), 3 = weight-gradient jobs (a_off, a_rows, a_half, b_off, b_rows, bias_layer, out_off,
+ * out_ld, out_row0, group).  index < 0: returns the number of entries; otherwise fills out[0..] (out_words >= 10) and returns
+ * the number of words written, or -1. */
+int nfb_debug_schedule(int which, int index, uint32_t* out, int out_words);
+
 /* Number of kernel launches issued by this handle so far (all kernels of this library). */
 int nfb_launch_count(NfbHandle* h, long long* out);
 

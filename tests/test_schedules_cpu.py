@@ -1,0 +1,109 @@
+"""Host-only checks of the compile-time schedules the kernels execute (nfb_debug_schedule): every weight byte of the packed
+streams is consumed exactly once per tile by each render program and by the backward chain, units fit their ring slots, TMEM
+operand columns stay inside their regions, and the weight-gradient jobs tile the accumulator space without overlap.  These are
+the invariants a change to csrc/nfb_layout.h or to one of the program builders can silently break; no GPU involved."""
+import ctypes as C
+
+import pytest
+
+STREAM_X1 = 864256      # nfb_layout.h kStreamBytesX1
+STREAM_BWD = 835584     # kBwdStreamBytes
+REC_BYTES = 1 << 20
+ACC_FLOATS = 499204     # kAccFloats
+
+
+@pytest.fixture(scope="module")
+def lib(built_lib):
+    lb = C.CDLL(built_lib)
+    lb.nfb_debug_schedule.restype = C.c_int
+    lb.nfb_debug_schedule.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int]
+    return lb
+
+
+def entries(lib, which):
+    n = lib.nfb_debug_schedule(which, -1, None, 0)
+    assert n > 0
+    out = []
+    buf = (C.c_uint32 * 10)()
+    for i in range(n):
+        w = lib.nfb_debug_schedule(which, i, buf, 10)
+        assert w > 0
+        out.append([int(buf[k]) for k in range(w)])
+    assert lib.nfb_debug_schedule(which, n, buf, 10) == -1
+    return out
+
+
+def spans(ents):
+    return [((e[3] & 0xFFFFF) << 4, (e[3] >> 20) * 128) for e in ents]
+
+
+def idesc_n(x):
+    return ((x >> 17) & 0x3F) << 3
+
+
+def assert_exact_cover(sp, total):
+    sp = sorted(sp)
+    pos = 0
+    for off, nbytes in sp:
+        assert off == pos, (off, pos)
+        pos += nbytes
+    assert pos == total
+
+
+def test_one_tile_program_covers_the_weight_stream(lib):
+    ents = entries(lib, 0)
+    assert len(ents) == 32
+    sp = spans(ents)
+    assert_exact_cover(sp, STREAM_X1)
+    for e, (off, nbytes) in zip(ents, sp):
+        assert nbytes <= 32768 and off % 1024 == 0          # one ring slot, swizzle-aligned
+        assert idesc_n(e[0]) * 128 == nbytes                 # MMA N == rows of the unit
+        d_col, a_col = e[1] & 0xFFFF, e[1] >> 16
+        assert d_col in (0, 256) and (e[2] & 1 or (a_col ^ d_col) & 256)   # operand and accumulator in different regions
+    assert sum(1 for e in ents if e[2] & 16) == 10           # one "accumulator complete" commit per step
+
+
+def test_two_tile_program_covers_the_weight_stream_in_half_units(lib):
+    ents = entries(lib, 1)
+    assert len(ents) == 58
+    sp = spans(ents)
+    assert_exact_cover(sp, STREAM_X1)                        # each half-unit once per tile pair
+    groups = {}
+    for e, (off, nbytes) in zip(ents, sp):
+        assert nbytes in (16384, 2048) and off % 16 == 0     # N = 128 or 16 rows of 128 bytes
+        assert idesc_n(e[0]) * 128 == nbytes
+        assert e[1] in (0, 32, 64, 96) or (e[2] & 1)         # K atom inside the 128-column operand region
+        groups.setdefault(e[4], []).append(e)
+    assert len(groups) == 17
+    for g in groups.values():
+        assert g[0][2] & 2 and g[-1][2] & 4 and len(g) <= 5  # first / last flags; a group never exceeds half the 10-slot ring
+        assert all(not (e[2] & 2) for e in g[1:]) and all(not (e[2] & 4) for e in g[:-1])
+
+
+def test_backward_chain_program(lib):
+    ents = entries(lib, 2)
+    assert len(ents) == 28
+    assert_exact_cover(spans(ents), STREAM_BWD)
+    for e in ents:
+        assert idesc_n(e[0]) in (128, 256)
+    assert sum(1 for e in ents if e[2] & 16) == 9            # nine steps
+
+
+def test_weight_gradient_jobs(lib):
+    jobs = entries(lib, 3)
+    assert len(jobs) == 21
+    used = []
+    for a_off, a_rows, a_half, b_off, b_rows, bias_layer, out_off, out_ld, out_row0, group in jobs:
+        bias_layer = bias_layer - (1 << 32) if bias_layer >= (1 << 31) else bias_layer   # -1 = no bias, sent as uint32
+        assert 0 <= a_off and a_off + 2 * a_rows * 128 <= REC_BYTES and a_rows in (128, 256) and a_half * 128 < a_rows
+        assert 0 <= b_off and b_off + 2 * b_rows * 128 <= REC_BYTES and b_rows in (16, 32, 64, 128, 256) and b_rows == out_ld
+        assert -1 <= bias_layer <= 8 and 0 <= group < 4
+        lo = out_off + out_row0 * out_ld
+        used.append((lo, lo + 128 * out_ld))
+    used.sort()
+    for (a0, a1), (b0, b1) in zip(used, used[1:]):
+        assert a1 <= b0, "weight-gradient jobs overlap in the accumulator space"
+    assert used[-1][1] <= ACC_FLOATS
+    biased = [j[5] for j in jobs if j[5] < (1 << 31)]
+    assert sorted(set(biased)) == list(range(9))                         # every layer's bias is produced ...
+    assert len([b for b in biased if b <= 5]) == 12                      # ... by both halves of the 256-wide layers, once each
