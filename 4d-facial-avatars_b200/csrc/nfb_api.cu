@@ -36,6 +36,7 @@ struct NfbHandle {
   nfb::NetBuffers net[2];
   bool frame_set = false;
   bool use_render2 = true;
+  bool train_render2 = false;
   long long launches = 0;
   // cached torch.linspace(0,1,n) tables on the device
   float* lin_c = nullptr; int lin_c_n = 0;
@@ -136,6 +137,10 @@ int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
   {  // NFB_KERNEL=v4 forces the one-tile-in-flight kernel everywhere (default: the two-tile kernel where it applies)
     const char* k = std::getenv("NFB_KERNEL");
     h->use_render2 = !(k && std::strcmp(k, "v4") == 0);
+    // The training forward defaults to the one-tile kernel: with the record stores the two-tile kernel's row warps spill
+    // (216 B) and it is slower there (measured 1.46 ms vs 1.01 ms per 2048-ray forward); NFB_TRAIN_KERNEL=v6 selects it.
+    const char* tk = std::getenv("NFB_TRAIN_KERNEL");
+    h->train_render2 = tk && std::strcmp(tk, "v6") == 0;
   }
   *out = h;
   return NFB_OK;
@@ -284,9 +289,9 @@ static int render_impl(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm,
     tr.n_rays = rays->n_rays; tr.nc = nc; tr.nf = nf; tr.rays_per_unit = p.rays_per_unit; tr.tiles_c = p.tiles_c;
     tr.tiles_f = p.tiles_f; tr.n_units = p.n_units; tr.has_bg = rays->background != nullptr; tr.white_bkgd = p.white_bkgd;
   }
-  // fast evaluation runs the two-tiles-in-flight kernel; exact mode (hi+lo operands need twice the TMEM columns), the
-  // training forward (records) and the debug probes run the one-tile kernel
-  const bool two_tile = h->use_render2 && !exact && !train && !p.dbg_act;
+  // fast-mode evaluation runs the two-tiles-in-flight kernel (the training forward only on request, see nfb_create); exact
+  // mode (hi+lo operands need twice the TMEM columns) and the layer probe run the one-tile kernel
+  const bool two_tile = h->use_render2 && !exact && !p.dbg_act && (!train || h->train_render2);
   if (two_tile) NFB_CUDA(nfb::launch_render2(p, h->num_sms, st, &h->launches));
   else NFB_CUDA(nfb::launch_render(p, exact ? 1 : 0, h->num_sms, st, &h->launches));
   if (train) h->tr.valid = true;

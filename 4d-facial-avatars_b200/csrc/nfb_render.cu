@@ -1,4 +1,6 @@
-// nfb_render.cu — the per-ray hot path as ONE persistent sm_100a kernel.
+// nfb_render.cu — the per-ray hot path as ONE persistent sm_100a kernel, ONE tile in flight per SM.  This is the kernel for
+// exact mode (FP16 hi+lo operands), the training forward (SAVE: also writes the activation records the backward reads) and
+// the debug probes; fast-mode evaluation runs the two-tiles-in-flight variant in nfb_render2.cu.
 //
 // Reference path replaced (nerface_code/nerf-pytorch/nerf/):
 //   train_utils.py:36-162  predict_and_render_radiance   (sampling, coarse->fine control flow)
@@ -13,7 +15,7 @@
 // Per tile the MLP is 10 GEMM steps (nfb_layout.h).  TMEM holds two 256-column regions used alternately: step s
 // accumulates (FP32) into one while its A operand — the previous step's output, converted IN PLACE to FP16 by the
 // epilogue — is read from the other; hidden activations never leave TMEM.  Weights stream L2 -> shared memory through
-// the bulk-copy (TMA) engine into a 4-slot ring of pre-swizzled 32 KB units ([N rows x 64 K]); the two CTAs of a
+// the bulk-copy (TMA) engine into a 5-slot ring (4 in exact mode) of pre-swizzled 32 KB units ([N rows x 64 K]); the two CTAs of a
 // cluster take turns issuing each copy as a cluster multicast, so every weight byte is read from L2 once per SM pair.
 // The epilogue converts and signals the accumulator in two column halves, and the units of the next step are ordered
 // so that the MMAs needing only the first half are issued while the second half is still being converted.
@@ -43,7 +45,7 @@ constexpr int kThreads = 320;   // producer warp + MMA warp + 8 row warps
 #endif
 constexpr int kCluster = NFB_CLUSTER;  // CTAs (SMs) per cluster sharing every weight unit through one multicast L2 read
 constexpr int kRowThreads = 256;
-constexpr uint32_t kRowBarrier = 1;  // named barrier id of the four row warps
+constexpr uint32_t kRowBarrier = 1;  // named barrier id of the eight row warps
 
 // TMEM column map (512 columns x 128 lanes x 32 bit): two 256-column regions used alternately.  Step s
 // accumulates into region (s & 1): half 0 in its columns [0,128), half 1 in [128,256).  The epilogue converts each
@@ -150,20 +152,6 @@ __device__ __forceinline__ void epi_half(uint32_t t_slice, uint32_t bias, uint32
     tmem_st16(t_slice + 48, lb);
   }
 }
-
-// ReLU mask of 32 post-activation FP16 values (bit j = feature j is non-zero).  An activation that is positive in FP32
-// but rounds to FP16 zero counts as inactive: its value is what the next layer saw.
-__device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&h)[16]) {
-  uint32_t m = 0u;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    m |= ((h[j] & 0xFFFFu) ? 1u : 0u) << (2 * j);
-    m |= ((h[j] >> 16) ? 1u : 0u) << (2 * j + 1);
-  }
-  return m;
-}
-
-__device__ __forceinline__ uint32_t cta_rank_early() { return cluster_ctarank(); }
 
 // ------------------------------------------------------------------------------------------------
 template <bool EXACT, bool SAVE>

@@ -25,6 +25,7 @@
 #include "nfb_layout.h"
 #include "nfb_ptx.cuh"
 #include "nfb_render_common.cuh"
+#include "nfb_save.cuh"
 
 namespace nfb {
 namespace v6 {
@@ -158,7 +159,7 @@ __device__ __forceinline__ void store32(uint32_t t_p, const uint32_t (&h)[32]) {
 // Sample depth + positional encoding of tile t of stream x -> PE buffer x (63 lanes + zero pad, FP16, swizzled).
 __device__ NFB_V6_PROLOGUE_ATTR void prologue_fn(const RenderParams& p, const RayP* __restrict__ rayp, float* __restrict__ carry_z,
                                                  uint8_t* __restrict__ pe_base, int x, int t, int pass, int S, int rows, int R,
-                                                 int row, int ch) {
+                                                 int row, int ch, uint8_t* __restrict__ rec /* training record of this tile or null */) {
     const int prow = t * 128 + row;
     const bool live = prow < rows;
     const int r = live ? prow / S : 0;
@@ -220,17 +221,22 @@ __device__ NFB_V6_PROLOGUE_ATTR void prologue_fn(const RenderParams& p, const Ra
       f[31] = 0.f;
     }
     uint8_t* pe = pe_base + x * (kTileM * 128);
+    uint32_t hh[16];
 #pragma unroll
     for (int qq = 0; qq < 4; ++qq) {
-      uint32_t hi[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) hi[e] = pack_f16x2(f[qq * 8 + 2 * e], f[qq * 8 + 2 * e + 1]);
+      for (int e = 0; e < 4; ++e) hh[qq * 4 + e] = pack_f16x2(f[qq * 8 + 2 * e], f[qq * 8 + 2 * e + 1]);
       const int off = row * 128 + (((ch * 4 + qq) ^ (row & 7)) << 4);
-      *reinterpret_cast<uint4*>(pe + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(pe + off) = make_uint4(hh[qq * 4], hh[qq * 4 + 1], hh[qq * 4 + 2], hh[qq * 4 + 3]);
     }
     fence_proxy_async_smem();
+    if (rec) store_t32(rec + kRecPE + img_row_base(64, row), row, 32 * ch, hh);  // transposed FP16 image for the weight gradients
 }
 
+// SAVE = training forward: also writes the per-tile activation records (nfb_layout.h kRec*), the per-sample colours / ReLU
+// inputs of sigma and |d| that nfb_render_backward reads.  Records are indexed like the one-tile kernel's: the stream x of
+// super-unit U is unit 2U + x there.
+template <bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_constant__ RenderParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -471,6 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
           rp.dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
           if (has_bg) { rp.bg[0] = p.bg[3 * g]; rp.bg[1] = p.bg[3 * g + 1]; rp.bg[2] = p.bg[3 * g + 2]; }
           rp.dz = p.dir_z ? p.dir_z[g] : d2;
+          if constexpr (SAVE) p.save_dnorm[g] = rp.dnorm;
         } else {
           for (int k = 0; k < 3; ++k) { rp.o[k] = 0.f; rp.d[k] = 0.f; rp.bg[k] = 0.f; }
           rp.dnorm = 0.f;
@@ -499,7 +506,15 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
         if (p.nf > 0 || it == 0)  // bias block of this pass's network (published by the barrier after the first prologue)
           for (int k = etid; k < kBiasFloats; k += kRowThreads) bias_s[k] = p.bias[pass][k];
 
-        auto prologue = [&](int x, int t) { prologue_fn(p, rayp, carry_z, smem + kOffPe, x, t, pass, S, rows, R, row, ch); };
+        // training record of tile t of stream x in this pass (null outside SAVE mode / beyond the last real unit)
+        auto tile_rec = [&](int x, int t) -> uint8_t* {
+          if constexpr (SAVE) {
+            const int u4 = 2 * unit + x;  // unit index in the one-tile kernel's numbering
+            if (u4 * R < p.n_rays) return p.save_rec + ((size_t)u4 * tiles_per_unit + (pass ? p.tiles_c : 0) + t) * kRecBytes;
+          }
+          return nullptr;
+        };
+        auto prologue = [&](int x, int t) { prologue_fn(p, rayp, carry_z, smem + kOffPe, x, t, pass, S, rows, R, row, ch, tile_rec(x, t)); };
 
         prologue(0, 0);
         prologue(1, 0);
@@ -515,6 +530,28 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
           if (lane == 0) {  // PE buffers of tile t are in place: first half-step of both streams may start
             mbar_arrive(bar_gate);
             mbar_arrive(bar_gate + 8);
+          }
+          uint8_t* rec0 = tile_rec(0, t);
+          uint8_t* rec1 = tile_rec(1, t);
+          if constexpr (SAVE) {  // direction encoding of each row's ray as a transposed image: features [16 ch, 16 ch + 16)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              uint8_t* rec = x ? rec1 : rec0;
+              if (rec) {
+                const RayP& rq = rayp[x * R + r];
+                uint8_t* img = rec + kRecPEd + img_row_base(32, row);
+                const uint32_t cr = (uint32_t)((row & 63) >> 3);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int ka = 16 * ch + 2 * e, kb = ka + 1;
+                  const float a = (live && rq.valid && ka < kDimDir) ? rq.ped[ka] : 0.f;
+                  const float b = (live && rq.valid && kb < kDimDir) ? rq.ped[kb] : 0.f;
+                  const uint32_t w = pack_f16x2(a, b);
+                  *reinterpret_cast<uint16_t*>(img + ka * 128 + ((cr ^ (uint32_t)(ka & 7)) << 4)) = (uint16_t)(w & 0xFFFFu);
+                  *reinterpret_cast<uint16_t*>(img + kb * 128 + ((cr ^ (uint32_t)(kb & 7)) << 4)) = (uint16_t)(w >> 16);
+                }
+              }
+            }
           }
           if (t == 0) {
             // per-ray additive term of layers_dir.0: W[:, 256:280] . PE_dir; thread = (output feature `row`, rays ch and ch+2)
@@ -549,6 +586,9 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                 tc_fence_after_sync();
                 tm.lap(10 + s);
                 uint32_t (&keep)[32] = x ? keep1 : keep0;
+                uint32_t hh[32];          // half-1 / single-half result (SAVE: written to the record after the gate)
+                int save_k0 = -1;         // SAVE: first feature of the 64 this event produced, -1: nothing to record
+                bool save_keep = false;   // SAVE: the 64 features are in `keep` (half 0) instead of `hh`
                 bool arrived = false;
                 float& sigma_raw = x ? sigma_raw1 : sigma_raw0;
                 const RayP& rp = rayp[x * R + r];
@@ -556,18 +596,20 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                   if (h == 0) {  // outputs [64 ch, +64) of features 0..127 -> registers (gate signalled inside)
                     epi_load64_early(t_q + c0, smem_u32(bias_n + si.bias_off + c0), 0u, keep, bar_gate + x * 8, lane);
                     arrived = true;
+                    save_k0 = c0; save_keep = true;
                   } else {       // P_x is dead: store half 0 (K atom ch), convert half 1 (K atom 2 + ch)
-                    uint32_t hh[32];
                     store32(t_p + 32 * ch, keep);
                     epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + 128 + c0), 0u, hh);
                     store32(t_p + 64 + 32 * ch, hh);
                     tmem_wait_st();
+                    save_k0 = 128 + c0;
                   }
                 } else if (s == 6) {
                   if (h == 0) {
                     epi_load64_early(t_q + c0, smem_u32(bias_n + si.bias_off + c0), smem_u32(dirbias + (x * R + r) * 128 + c0), keep,
                                      bar_gate + x * 8, lane);
                     arrived = true;
+                    save_k0 = c0; save_keep = true;
                   } else {  // sigma = column 0 of the 16-wide second half; then g0 becomes the operand (K = 128)
                     if (ch == 0) {
                       uint32_t v[4];
@@ -579,10 +621,10 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                     tmem_wait_st();
                   }
                 } else if (s <= 8) {  // 128 -> 128 layers: the MMAs that read P have completed
-                  uint32_t hh[32];
                   epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + c0), 0u, hh);
                   store32(t_p + 32 * ch, hh);
                   tmem_wait_st();
+                  save_k0 = c0;
                 } else if (ch == 0) {
                   // fc_rgb output: colour and sigma per sample for compositing (volume_rendering_utils.py:29-33, 41-53)
                   uint32_t v[4];
@@ -598,6 +640,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                     float sig = sigma_raw;
                     if (p.noise_std > 0.f && rp.valid)
                       sig = __fadd_rn(sig, __fmul_rn((pass ? p.noise_f : p.noise_c)[(size_t)rp.gidx * S + i], p.noise_std));
+                    const float sig_in = sig;  // what the ReLU sees (volume_rendering_utils.py:52)
                     sig = fmaxf(sig, 0.f);
                     float4 pre;
                     if (i == S - 1) {
@@ -611,12 +654,28 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                     }
                     pre.w = sig;
                     carry_raw[x * kRowsMax + prow] = pre;
+                    if constexpr (SAVE) {  // what the compositing backward needs: colour (or bg) and the ReLU input
+                      if (rp.valid) reinterpret_cast<float4*>(pass ? p.save_raw_f : p.save_raw_c)[(size_t)rp.gidx * S + i] = make_float4(pre.x, pre.y, pre.z, sig_in);
+                    }
                   }
                 }
                 if (s < kNumSteps - 1 && !arrived) {  // Q_x has been read (and, after a step's last half, P_x holds the next operand)
                   tc_fence_before_sync();
                   __syncwarp();
                   if (lane == 0) mbar_arrive(bar_gate + x * 8);
+                }
+                if constexpr (SAVE) {  // after the gate: activation image + ReLU mask of the 64 features this event produced
+                  uint8_t* rec = x ? rec1 : rec0;
+                  if (rec && save_k0 >= 0) {
+                    uint32_t a[16], b[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { a[j] = save_keep ? keep[j] : hh[j]; b[j] = save_keep ? keep[16 + j] : hh[16 + j]; }
+                    uint8_t* img = rec + rec_x_off(s) + img_row_base(rec_width(s), row);
+                    store_t32(img, row, save_k0, a);
+                    store_t32(img, row, save_k0 + 32, b);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(rec + kRecMask) + (s * 128 + row) * 8 + (save_k0 >> 5)) =
+                        make_uint2(relu_mask32(a), relu_mask32(b));
+                  }
                 }
                 tm.lap(20 + s);
               }
@@ -786,7 +845,9 @@ int debug_prog_v6(int index, uint32_t* out) {  // host copy of the half-step pro
 }
 
 cudaError_t render2_kernel_setup() {
-  return cudaFuncSetAttribute(v6::render2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v6::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(v6::render2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v6::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(v6::render2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v6::kSmemBytes);
 }
 
 // `p` is prepared for the one-tile kernel (n_units = units of R rays); here a unit of work is 2R rays.
@@ -809,7 +870,8 @@ cudaError_t launch_render2(const RenderParams& p_in, int num_sms, cudaStream_t s
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, v6::render2_kernel, p);
+  cudaError_t e = p.save_rec ? cudaLaunchKernelEx(&cfg, v6::render2_kernel<true>, p)   // training forward: writes the records
+                             : cudaLaunchKernelEx(&cfg, v6::render2_kernel<false>, p);
   ++*launches;
   return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -89,6 +89,20 @@ __device__ __forceinline__ void epi_math(const uint32_t (&v)[32], uint32_t bias,
   }
 }
 
+// ReLU mask of 32 post-activation FP16 values (bit j = feature j is non-zero).  An activation that is positive in FP32
+// but rounds to FP16 zero counts as inactive: its value is what the next layer saw.
+__device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&h)[16]) {
+  uint32_t m = 0u;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    m |= ((h[j] & 0xFFFFu) ? 1u : 0u) << (2 * j);
+    m |= ((h[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+  }
+  return m;
+}
+
+__device__ __forceinline__ uint32_t cta_rank_early() { return cluster_ctarank(); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -188,8 +188,6 @@ constexpr int kNumSlots = 5;
 constexpr int kThreads = 320;
 constexpr int kCluster = 2;
 constexpr int kRowThreads = 256;
-constexpr uint32_t kRowBarrier = 1;
-
 constexpr int kOffRing = 0;
 constexpr int kOffOp = kOffRing + kNumSlots * kMaxUnitBytes;  // d raw operand: [128 rows x 64 k] FP16, swizzled (k < 4 used)
 constexpr int kOffBars = kOffOp + kTileM * 128;
