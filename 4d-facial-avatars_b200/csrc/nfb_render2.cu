@@ -35,17 +35,11 @@ using Timer = PhaseTimer;
 constexpr int kNumSlots = 10;
 constexpr int kSlotBytes = 16384;
 constexpr int kRowsMax = 512;  // sample rows of one pass of one stream
-#ifndef NFB_V6_ISSUE
-#define NFB_V6_ISSUE 2   // weight units per elected MMA block (1 or 2)
-#endif
-#ifndef NFB_V6_DUAL
-#define NFB_V6_DUAL 1
-#endif
-// NFB_V6_DUAL=1 (default; measured 4.51 M rays/s against 4.37 M): one MMA-issuing warp per stream (warps 1 and 2, on different SM sub-partitions) instead of one warp
-// issuing both streams' groups in turn; the row warps then start at warp 4 (warp 3 idles) and every ring slot is released
-// by two commits per CTA.
-constexpr int kRowWarp0 = NFB_V6_DUAL ? 4 : 2;
-constexpr int kThreads = (kRowWarp0 + 8) * 32;  // producer warp + MMA warp(s) + 8 row warps
+constexpr int kIssueUnits = 2;  // weight units (4 MMAs each) per elected MMA block; 1 and 4 measured slower
+// Warps: 0 = weight producer, 1 / 2 = MMA issuer of stream X / Y (different SM sub-partitions; one warp issuing both streams
+// in turn measured 4.37 M rays/s against 4.51 M), 3 = idle, 4..11 = row warps.  12 warps still allow 168 registers per thread.
+constexpr int kRowWarp0 = 4;
+constexpr int kThreads = (kRowWarp0 + 8) * 32;
 #ifndef NFB_V6_CLUSTER
 #define NFB_V6_CLUSTER 2
 #endif
@@ -148,16 +142,8 @@ __device__ __forceinline__ void store32(uint32_t t_p, const uint32_t (&h)[32]) {
   tmem_st16(t_p + 16, b);
 }
 
-#ifndef NFB_V6_PROLOGUE_NOINLINE
-#define NFB_V6_PROLOGUE_NOINLINE 0
-#endif
-#if NFB_V6_PROLOGUE_NOINLINE
-#define NFB_V6_PROLOGUE_ATTR __noinline__
-#else
-#define NFB_V6_PROLOGUE_ATTR __forceinline__
-#endif
 // Sample depth + positional encoding of tile t of stream x -> PE buffer x (63 lanes + zero pad, FP16, swizzled).
-__device__ NFB_V6_PROLOGUE_ATTR void prologue_fn(const RenderParams& p, const RayP* __restrict__ rayp, float* __restrict__ carry_z,
+__device__ __forceinline__ void prologue_fn(const RenderParams& p, const RayP* __restrict__ rayp, float* __restrict__ carry_z,
                                                  uint8_t* __restrict__ pe_base, int x, int t, int pass, int S, int rows, int R,
                                                  int row, int ch, uint8_t* __restrict__ rec /* training record of this tile or null */) {
     const int prow = t * 128 + row;
@@ -253,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumSlots; ++i) {
       mbar_init(bar_full + i * 8, 1);
-      mbar_init(bar_empty + i * 8, (NFB_V6_DUAL ? 2 : 1) * kCluster);
+      mbar_init(bar_empty + i * 8, 2 * kCluster);
     }
     for (int x = 0; x < 2; ++x) {
       mbar_init(bar_gate + x * 8, kRowThreads / 32);
@@ -300,7 +286,6 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
         }
       }
     }
-#if NFB_V6_DUAL
   } else if (warp == 1 || warp == 2) {
     // ============================== MMA issuer of stream x = warp - 1 ==============================
     const int x = warp - 1;
@@ -315,8 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
           mbar_wait(bar_gate + x * 8, ph_gate);  // operand P_x in place, accumulator Q_x read
           ph_gate ^= 1;
           tc_fence_after_sync();
-          for (uint32_t j = 0; j < g_count; j += NFB_V6_ISSUE) {
-            const bool two = (NFB_V6_ISSUE == 2) && j + 1 < g_count;
+          for (uint32_t j = 0; j < g_count; j += kIssueUnits) {
+            const bool two = (kIssueUnits == 2) && j + 1 < g_count;
             const ProgEntry e0 = c_prog.e[g_first + j];
             const ProgEntry e1 = c_prog.e[g_first + (two ? j + 1 : j)];
             uint32_t sl1 = sl + 1, ph1 = ph;
@@ -350,83 +335,6 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
         }
       }
     }
-#else
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    uint32_t slot = 0, phase = 0;  // ring position at the start of the current group
-    uint32_t ph_gate0 = 0, ph_gate1 = 0;
-    const bool prof_on = NFB_TIMERS && p.prof != nullptr;
-    long long acc_gate = 0, acc_full = 0, acc_issue = 0, tq = prof_on ? clock64() : 0;
-    const uint64_t pe_desc0 = umma_smem_desc_sw128(smem_base + kOffPe);
-    const uint64_t pe_desc1 = umma_smem_desc_sw128(smem_base + kOffPe + kTileM * 128);
-    for (int it = 0; it < n_iter; ++it) {
-      for (int t = 0; t < tiles_per_unit; ++t) {
-        for (int g = 0; g < kNumGroups; ++g) {
-          const uint32_t g_first = c_prog.g[g].first, g_count = c_prog.g[g].count;
-          uint32_t sl = slot, ph = phase;
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            // stream x may run this half-step: its operand P_x is in place and its accumulator Q_x has been read
-            if (prof_on) { const long long tn = clock64(); acc_issue += tn - tq; tq = tn; }
-            if (x == 0) { mbar_wait(bar_gate, ph_gate0); ph_gate0 ^= 1; }
-            else        { mbar_wait(bar_gate + 8, ph_gate1); ph_gate1 ^= 1; }
-            tc_fence_after_sync();
-            if (prof_on) { const long long tn = clock64(); acc_gate += tn - tq; tq = tn; }
-            sl = slot; ph = phase;  // both streams walk the same ring slots
-            const uint32_t p_tmem = tmem_base + (uint32_t)x * 256u;
-            const uint32_t q_tmem = p_tmem + 128u;
-            const uint64_t pe_desc = x ? pe_desc1 : pe_desc0;
-            // Two weight units (8 MMAs) per elected block.  At N = 128 an MMA is short (about 75 cycles), so per-unit
-            // waits / elect / warp syncs bound the issue rate (tools/mma_mix.cu: 106 cycles per MMA with 4 per block, 78 with
-            // 8; worse while the row warps are busy): 2 units per block measured 4.38 M rays/s against 3.96 M with 1.  More
-            // per block is slower again (4 units: 3.54 M, whole group: 3.99 M) because the block then waits for all of its
-            // weight slots before the first MMA — the weights arrive just in time.  Everything the MMAs consume is computed
-            // outside the elected block so it stays in uniform registers.
-            for (uint32_t j = 0; j < g_count; j += 2) {
-              const bool two = j + 1 < g_count;
-              const ProgEntry e0 = c_prog.e[g_first + j];
-              const ProgEntry e1 = c_prog.e[g_first + (two ? j + 1 : j)];
-              uint32_t sl1 = sl + 1, ph1 = ph;
-              if (sl1 == kNumSlots) { sl1 = 0; ph1 ^= 1; }
-              if (x == 0) {  // stream Y reuses the slots stream X has just waited for
-                mbar_wait(bar_full + sl * 8, ph);
-                if (two) mbar_wait(bar_full + sl1 * 8, ph1);
-                tc_fence_after_sync();
-              }
-              const uint64_t b_desc0 = umma_smem_desc_sw128(smem_base + kOffRing + sl * kSlotBytes);
-              const uint64_t b_desc1 = umma_smem_desc_sw128(smem_base + kOffRing + sl1 * kSlotBytes);
-              if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t bd = b_desc0 + (uint64_t)(ks * 2);
-                  const uint32_t acc_flag = ((e0.z & kFirst) && ks == 0) ? 0u : 1u;
-                  if (e0.z & kFromPe) umma_ss(q_tmem, pe_desc + (uint64_t)(ks * 2), bd, e0.x, acc_flag);
-                  else umma_ts(q_tmem, p_tmem + e0.y + ks * 8, bd, e0.x, acc_flag);
-                }
-                if (x == 1) umma_commit_multicast(bar_empty + sl * 8, kAllCtas);  // both streams are done with the slot
-                if (two) {
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    umma_ts(q_tmem, p_tmem + e1.y + ks * 8, b_desc1 + (uint64_t)(ks * 2), e1.x, 1u);  // never the PE atom, never first
-                  if (x == 1) umma_commit_multicast(bar_empty + sl1 * 8, kAllCtas);
-                }
-                if ((two ? e1.z : e0.z) & kLast) umma_commit(bar_accfull + x * 8);
-              }
-              __syncwarp();
-              if (two) { sl = sl1; ph = ph1; }
-              if (++sl == kNumSlots) { sl = 0; ph ^= 1; }
-            }
-          }
-          slot = sl; phase = ph;
-        }
-      }
-    }
-    if (prof_on && lane == 0) {
-      atomicAdd(p.prof + 44, (unsigned long long)acc_issue);
-      atomicAdd(p.prof + 45, (unsigned long long)acc_gate);
-      atomicAdd(p.prof + 46, (unsigned long long)acc_full);
-    }
-#endif
   } else if (warp >= kRowWarp0) {
     // ============================== row warps ==============================
     const int q = warp & 3;
