@@ -35,6 +35,12 @@ using Timer = PhaseTimer;
 constexpr int kNumSlots = 10;
 constexpr int kSlotBytes = 16384;
 constexpr int kRowsMax = 512;  // sample rows of one pass of one stream
+#ifndef NFB_V6_HELPER
+#define NFB_V6_HELPER 1
+#endif
+// Warp 3 (otherwise idle) computes the positional encoding of the NEXT fine-pass tile of both streams while the row warps
+// run the current tile's epilogues; with 0 the row warps do it themselves after step 3 (tensor core idle meanwhile).
+constexpr bool kHelper = NFB_V6_HELPER != 0;
 constexpr int kIssueUnits = 2;  // weight units (4 MMAs each) per elected MMA block; 1 and 4 measured slower
 // Warps: 0 = weight producer, 1 / 2 = MMA issuer of stream X / Y (different SM sub-partitions; one warp issuing both streams
 // in turn measured 4.37 M rays/s against 4.51 M), 3 = idle, 4..11 = row warps.  12 warps still allow 168 registers per thread.
@@ -62,7 +68,7 @@ constexpr int kOffZ = kOffRaw + 2 * kRowsMax * 16;
 constexpr int kOffDirBias = kOffZ + 2 * kRowsMax * 4;         // [4 rays][128]
 constexpr int kOffRay = kOffDirBias + 4 * 128 * 4;
 constexpr int kOffBars = kOffRay + 4 * kRayFloats * 4;
-constexpr int kNumBars = 2 * kNumSlots + 4;                   // full[] empty[] gate[2] accfull[2]
+constexpr int kNumBars = 2 * kNumSlots + 8;                   // full[] empty[] gate[2] accfull[2] pefree[2] peready[2]
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0, "alignment");
@@ -105,6 +111,14 @@ constexpr ProgTable make_prog() {
 constexpr ProgTable kProgHost = make_prog();
 static_assert(kProgHost.n_entries <= kMaxProg && kProgHost.n_groups <= kMaxGroups, "program table too small");
 constexpr int kNumGroups = kProgHost.n_groups;    // 17
+constexpr int last_pe_group() {  // the last half-step group whose first unit is the PE atom (step 3, half 1)
+  int last = -1;
+  for (int g = 0; g < kProgHost.n_groups; ++g)
+    if (kProgHost.e[kProgHost.g[g].first].z & kFromPe) last = g;
+  return last;
+}
+constexpr int kLastPeGroup = last_pe_group();
+static_assert(kLastPeGroup == 7, "step 3, half 1");
 constexpr int kNumEntries = kProgHost.n_entries;  // 58
 __constant__ ProgTable c_prog = make_prog();
 
@@ -233,6 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
   const uint32_t bar_empty = bar_full + kNumSlots * 8;       // [kNumSlots]
   const uint32_t bar_gate = bar_empty + kNumSlots * 8;       // [2] stream x: operand / accumulator ready for its next half-step
   const uint32_t bar_accfull = bar_gate + 16;                // [2] stream x: half-step accumulator complete
+  const uint32_t bar_pefree = bar_accfull + 16;              // [2] stream x: the MMAs reading PE buffer x (steps 0, 3) are done
+  const uint32_t bar_peready = bar_pefree + 16;              // [2] stream x: the helper warp has encoded the next tile into it
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
 
@@ -244,6 +260,8 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
     for (int x = 0; x < 2; ++x) {
       mbar_init(bar_gate + x * 8, kRowThreads / 32);
       mbar_init(bar_accfull + x * 8, 1);
+      mbar_init(bar_pefree + x * 8, 1);
+      mbar_init(bar_peready + x * 8, 1);
     }
     mbar_fence_init();
   }
@@ -293,8 +311,14 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
     const uint32_t p_tmem = tmem_base + (uint32_t)x * 256u;
     const uint32_t q_tmem = p_tmem + 128u;
     const uint64_t pe_desc = umma_smem_desc_sw128(smem_base + kOffPe + x * (kTileM * 128));
+    uint32_t ph_per = 0;
     for (int it = 0; it < n_iter; ++it) {
       for (int t = 0; t < tiles_per_unit; ++t) {
+        const bool fine_t = kHelper && t >= p.tiles_c;  // fine-pass tiles: PE buffer handshake with the helper warp
+        if (fine_t && t > p.tiles_c) {                  // its encoding was written by the helper, not by the row warps
+          mbar_wait(bar_peready + x * 8, ph_per);
+          ph_per ^= 1;
+        }
         for (int g = 0; g < kNumGroups; ++g) {
           const uint32_t g_first = c_prog.g[g].first, g_count = c_prog.g[g].count;
           mbar_wait(bar_gate + x * 8, ph_gate);  // operand P_x in place, accumulator Q_x read
@@ -331,6 +355,41 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
             __syncwarp();
             if (two) { sl = sl1; ph = ph1; }
             if (++sl == kNumSlots) { sl = 0; ph ^= 1; }
+          }
+          if (fine_t && g == kLastPeGroup) {  // step 3's second half issued: nothing reads PE buffer x after these MMAs
+            if (elect_one()) umma_commit(bar_pefree + x * 8);
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (kHelper && warp == 3) {
+    // ============================== helper: encoding of the next fine-pass tile ==============================
+    if (p.nf > 0) {
+      const RayP* rayp = reinterpret_cast<const RayP*>(smem + kOffRay);
+      float* carry_z = reinterpret_cast<float*>(smem + kOffZ);
+      const int R = p.rays_per_unit, S = p.s_fine, rows = R * S, n_tiles = p.tiles_f;
+      uint32_t ph_free0 = 0, ph_free1 = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int unit = blockIdx.x + it * gridDim.x;
+        for (int t = 0; t < n_tiles; ++t) {
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            if (x == 0) { mbar_wait(bar_pefree, ph_free0); ph_free0 ^= 1; }
+            else        { mbar_wait(bar_pefree + 8, ph_free1); ph_free1 ^= 1; }
+            if (t + 1 < n_tiles) {
+              uint8_t* rec = nullptr;
+              if constexpr (SAVE) {
+                const int u4 = 2 * unit + x;
+                if (u4 * R < p.n_rays) rec = p.save_rec + ((size_t)u4 * tiles_per_unit + p.tiles_c + (t + 1)) * kRecBytes;
+              }
+              for (int k = 0; k < 8; ++k) {  // 128 rows x 2 lane halves = 256 thread-tasks for 32 threads
+                const int idx = k * 32 + lane;
+                prologue_fn(p, rayp, carry_z, smem + kOffPe, x, t + 1, 1, S, rows, R, idx & 127, idx >> 7, rec);
+              }
+              __syncwarp();  // every lane has fenced its generic-proxy stores (inside prologue_fn)
+              if (lane == 0) mbar_arrive(bar_peready + x * 8);
+            }
           }
         }
       }
@@ -588,7 +647,8 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
                 tm.lap(20 + s);
               }
             }
-            if (s == 3 && t + 1 < n_tiles) {  // both PE buffers are free: encode the next tile pair under steps 4..9
+            if (s == 3 && t + 1 < n_tiles && !(kHelper && pass == 1)) {  // both PE buffers are free: encode the next tile pair
+                                                                         // under steps 4..9 (fine pass: the helper warp does it)
               prologue(0, t + 1);
               prologue(1, t + 1);
               tm.lap(2);
