@@ -63,3 +63,74 @@ def allreduce_gradients(params, group=None, average=True):
         g.copy_(flat[off:off + n].view_as(g))
         off += n
     return flat.numel()
+
+
+class _ScaleGrad(torch.autograd.Function):
+    """Identity whose gradient is multiplied by `factor` (see data_parallel: local rows count `world` times under an
+    AVERAGING gradient all-reduce, so that terms every rank computes identically — the latent regulariser — stay right)."""
+
+    @staticmethod
+    def forward(ctx, x, factor):
+        ctx.factor = factor
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.factor, None
+
+
+def _gather_cat(local: torch.Tensor, group=None):
+    """All-gather equal-sized shards along dim 0 (values only, no gradient)."""
+    world = dist.get_world_size(group)
+    out = local.new_empty((world * local.shape[0],) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, local.detach().contiguous(), group=group)
+    return out
+
+
+def data_parallel(run_fn, group=None):
+    """Wrap a function with the signature of run_one_iter_of_nerf (train_utils.py:165-181) so that an UNMODIFIED caller
+    (train_transformed_rays.py:336-352, eval_transformed_rays.py:449-467) runs it data-parallel, one process per GPU:
+
+    * mode == "validation": the [H, W, 3] ray bundle (and background / ablation directions) is split into contiguous row
+      blocks (shard_rows), each rank renders its block, and every output is all-gathered back to [H, W, ...].
+    * mode == "train": the [N, 3] ray batch is split evenly (shard_batch); every rank renders its shard and receives the
+      other shards' outputs by all-gather, so the caller's loss over the FULL batch is unchanged.  Only the local rows carry
+      gradient, scaled by the world size, so that an averaging all-reduce of the parameter gradients
+      (allreduce_gradients(average=True), e.g. from an optimizer pre-step hook) yields exactly the single-process gradient —
+      including loss terms that do not depend on the rays (the latent-code regulariser), which every rank computes alike.
+
+    Noise: each rank draws its own shard's noise, so stochastic runs match the single-process run in distribution only."""
+    def wrapped(height, width, focal_length, model_coarse, model_fine, ray_origins, ray_directions, options, mode="train",
+                encode_position_fn=None, encode_direction_fn=None, expressions=None, background_prior=None, latent_code=None,
+                ray_directions_ablation=None):
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            return run_fn(height, width, focal_length, model_coarse, model_fine, ray_origins, ray_directions, options, mode,
+                          encode_position_fn, encode_direction_fn, expressions, background_prior, latent_code, ray_directions_ablation)
+        rank = dist.get_rank(group)
+        if mode == "validation":
+            H, W = ray_directions.shape[0], ray_directions.shape[1]
+            begin, rows = shard_rows(H, world, rank)
+            sl = slice(begin, begin + rows)
+            bg = background_prior.reshape(H, W, 3)[sl].reshape(-1, 3) if background_prior is not None else None
+            abl = ray_directions_ablation.reshape(H, W, 3)[sl] if torch.is_tensor(ray_directions_ablation) else ray_directions_ablation
+            outs = run_fn(rows, width, focal_length, model_coarse, model_fine, ray_origins[sl], ray_directions[sl], options, mode,
+                          encode_position_fn, encode_direction_fn, expressions, bg, latent_code, abl)
+            return tuple(gather_rows(o.contiguous(), H, group) if o is not None else None for o in outs)
+        n = ray_directions.shape[0]
+        begin, per = shard_batch(n, world, rank)
+        sl = slice(begin, begin + per)
+        bg = background_prior[sl] if background_prior is not None else None
+        abl = ray_directions_ablation[sl] if torch.is_tensor(ray_directions_ablation) else ray_directions_ablation
+        outs = run_fn(height, width, focal_length, model_coarse, model_fine, ray_origins[sl], ray_directions[sl], options, mode,
+                      encode_position_fn, encode_direction_fn, expressions, bg, latent_code, abl)
+        full = []
+        for o in outs:
+            if o is None:
+                full.append(None)
+                continue
+            g = _gather_cat(o, group)
+            local = _ScaleGrad.apply(o, float(world)) if o.requires_grad else o
+            full.append(torch.cat((g[:begin], local, g[begin + per:]), dim=0))
+        return tuple(full)
+    return wrapped

@@ -3,6 +3,15 @@ drop-in `nerf` package of this repo first on sys.path.  Provide
 `matplotlib` when those packages are absent (the scripts import them before `nerf`).
 
     python 4d-facial-avatars_b200/run_reference_script.py <script.py> [script args...]
+
+Data-parallel, one process per GPU of one node, the script body still unmodified:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \\
+        4d-facial-avatars_b200/run_reference_script.py <script.py> [script args...]
+
+Under torchrun (WORLD_SIZE > 1) the launcher initialises NCCL, pins the rank's GPU, replaces `nerf.run_one_iter_of_nerf` by
+its ray-sharding wrapper (nerf/parallel.py: data_parallel), averages the parameter gradients in a flat bucket before
+every optimizer step (a global optimizer pre-step hook), and lets only rank 0 write images / checkpoints / summaries.
 """
 import os
 import runpy
@@ -63,6 +72,36 @@ def _ensure_matplotlib():
     sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
 
 
+def _enable_data_parallel():
+    """One process per GPU under torchrun: shard rays inside run_one_iter_of_nerf, average gradients before optimizer steps,
+    rank-0-only output files."""
+    import torch
+    import torch.distributed as dist
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import nerf
+    from nerf import parallel
+    nerf.run_one_iter_of_nerf = parallel.data_parallel(nerf.run_one_iter_of_nerf)
+    nerf.train_utils.run_one_iter_of_nerf = nerf.run_one_iter_of_nerf
+
+    def _avg_grads(optimizer, args, kwargs):
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        parallel.allreduce_gradients(params, average=True)
+    torch.optim.optimizer.register_optimizer_step_pre_hook(_avg_grads)
+    if rank != 0:  # only rank 0 writes files
+        import imageio
+        imageio.imwrite = imageio.imsave = lambda *a, **k: None
+        torch.save = lambda *a, **k: None
+        try:
+            from torch.utils import tensorboard
+            for name in ("add_scalar", "add_image", "add_images", "add_histogram"):
+                setattr(tensorboard.SummaryWriter, name, lambda *a, **k: None)
+        except Exception:
+            pass
+    return world
+
+
 def main():
     if len(sys.argv) < 2:
         sys.exit(__doc__)
@@ -70,6 +109,8 @@ def main():
     _ensure_imageio()
     _ensure_matplotlib()
     sys.path.insert(0, HERE)  # the drop-in `nerf` wins over the one next to the script
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        _enable_data_parallel()
     sys.argv = [script] + sys.argv[2:]
     os.chdir(os.path.dirname(script))
     runpy.run_path(script, run_name="__main__")
