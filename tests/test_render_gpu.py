@@ -118,6 +118,33 @@ def test_dropin_api_validation_and_arity(env, precision):
     nerf.set_precision("fast")
 
 
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+@pytest.mark.parametrize("nc,nf", [(128, 64), (100, 60), (200, 300), (40, 24)], ids=["128c64f", "100c60f", "200c300f", "40c24f"])
+def test_sample_counts_against_oracle(env, precision, nc, nf):
+    """Tile shapes the golden cases do not hit: two coarse tiles per ray pair (128c), sample counts that are not multiples of
+    anything (partially filled last tiles), one ray per stream with four fine tiles (200c+300f), and a pass smaller than
+    one tile.  13 rays: odd, so the last unit of work is only partly valid in both kernels."""
+    nerf, _engine, dev = env
+    n = 13
+    fr = O.synthetic_frame(5, 4, 4)
+    ro, rd = O.ray_bundle(4, 4, fr["intrinsics"], fr["pose"])
+    ro, rd = ro.reshape(-1, 3)[:n].contiguous(), rd.reshape(-1, 3)[:n].contiguous()
+    bg = fr["bg"].reshape(-1, 3)[:n].contiguous()
+    pc, pf = O.random_init_params(100), O.random_init_params(101)
+    mc, mf = make_model(nerf, pc, dev), make_model(nerf, pf, dev)
+    eng = _engine.renderer_for(dev)
+    eng.sync_weights(mc, mf)
+    eng.set_frame(fr["expr"].to(dev), fr["latent"].to(dev))
+    out = eng.render(ro.to(dev), rd.to(dev), 0.2, 0.8, nc, nf, background=bg.to(dev), precision=precision)
+    torch.cuda.synchronize()
+    rays = torch.cat((ro, rd, torch.full((n, 1), 0.2), torch.full((n, 1), 0.8)), dim=-1)
+    with torch.no_grad():
+        ref = O.render_chunk(rays, pc, pf, O.Sampling(nc, nf), fr["expr"], fr["latent"], bg, O.Noise())
+    for name, r in zip(NAMES, ref):
+        err = float((out[name].cpu() - r).abs().max())
+        assert err < 1e-4, (name, err)
+
+
 def test_in_kernel_ray_generation_matches_explicit_rays(env):
     nerf, _engine, dev = env
     H, W = 16, 24
