@@ -1,9 +1,9 @@
-// nfb_render2.cu — the render path with TWO tiles in flight per SM (fast mode, evaluation).
+// nfb_render2.cu — the render path with TWO tiles in flight per SM (fast mode: evaluation; training variant on request).
 //
 // Same reference path and same per-tile algebra as nfb_render.cu (see its header for the reference citations); what
 // changes is how the tensor core is kept busy.  With one tile per SM the epilogue -> MMA hand-off of every step is
 // exposed (the tensor pipe is busy about a third of the time).  Here every CTA runs two tile "streams" X and Y in lock
-// step, and every MLP step is issued as N=128 half-steps in the order  X.h0  Y.h0  X.h1  Y.h1 :
+// step, and every MLP step is issued as N=128 half-steps, which the gates order as  X.h0  Y.h0  X.h1  Y.h1 :
 //
 //   * TMEM (512 columns): stream x owns P_x = [256x, 256x+128): the FP16 A operand (K <= 256 = 4 atoms of 32 columns) and
 //     Q_x = [256x+128, 256x+256): the FP32 accumulator of one half-step (N = 128).  Both halves of a step read P_x, so
@@ -14,7 +14,11 @@
 //     epilogue has one half-step (16 MMAs) of the other stream to hide under.
 //   * Both streams use the same weights back to back, so a weight half-unit ([128 rows x 64 K] = 16 KB, a contiguous
 //     half of the unit the packed stream already holds) is loaded ONCE per tile pair: L2 -> SM weight traffic per tile
-//     halves.  Ring = 8 slots x 16 KB; a slot is released (cluster-multicast commit) after stream Y has used it.
+//     halves.  Ring = 10 slots x 16 KB; a slot is released (cluster-multicast commits) when both streams have used it.
+//
+// Warps (384 threads): 0 = weight producer; 1, 2 = MMA issuers of streams X, Y (two weight units = 8 MMAs per elected
+// block); 3 = helper that encodes the NEXT fine-pass tile of both streams into the PE buffers while the current tile runs;
+// 4..11 = row warps (thread <-> sample row, two warps per TMEM lane quadrant splitting the columns) serving both streams.
 //
 // A unit of work is 2R rays (R = 2, or 1 when one ray fills the pass): rays [0,R) form stream X, rays [R,2R) stream Y;
 // sampling, compositing, inverse-CDF resampling and the sort run for all 2R rays between the passes as in nfb_render.cu.
