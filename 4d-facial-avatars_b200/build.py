@@ -1,7 +1,10 @@
 """Build lib/libnfb.so (the C-ABI shared library of include/nfb.h) in-tree with nvcc for sm_100a.
 
 The .so is git-ignored but travels to the GPU box with the repo snapshot.  Rebuilds only when a
-source is newer than the library.  Usage: python 4d-facial-avatars_b200/build.py [--force] [--verbose]
+source is newer than the library.  Usage: python 4d-facial-avatars_b200/build.py [--force] [--verbose] [--timers]
+
+--timers additionally builds lib/libnfb_timers.so with the phase timers compiled in (-DNFB_TIMERS=1; they cost registers in
+the kernels' hot loops, so the product library does not carry them); tools/phase_profile.py loads it through NFB_LIB.
 """
 import os
 import subprocess
@@ -30,24 +33,26 @@ def needs_build():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, timers=False):
+    out = os.path.join(LIB_DIR, "libnfb_timers.so") if timers else LIB
+    if not timers and not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-DNFB_BUILD",
-           "-o", LIB] + srcs
+           "-Xcompiler", "-fPIC", "-shared", "-DNFB_BUILD"] + (["-DNFB_TIMERS=1"] if timers else []) + ["-o", out] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libnfb.so")
+        raise RuntimeError("nvcc failed building " + os.path.basename(out))
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--timers" in sys.argv:
+        print(build(verbose="--verbose" in sys.argv, timers=True))

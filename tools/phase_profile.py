@@ -1,6 +1,14 @@
-"""Phase-cycle profile of the render kernel (NfbDebug.prof).  Usage: python tools/phase_profile.py [fast|exact] [H W]"""
+"""Phase-cycle profile of the render kernels (NfbDebug.prof).  Usage: python tools/phase_profile.py [fast|exact] [H W]
+
+Needs a library with the timers compiled in: `python 4d-facial-avatars_b200/build.py --timers` (lib/libnfb_timers.so, picked
+up here unless NFB_LIB is set).  NFB_KERNEL=v4 profiles the one-tile kernel in fast mode.  In the two-tile kernel the slots
+"wait MMA step s" / "epilogue step s" sum all half-step events (both halves, both streams) of step s."""
 import os
 import sys
+
+_timers = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "4d-facial-avatars_b200", "lib", "libnfb_timers.so")
+if "NFB_LIB" not in os.environ and os.path.exists(_timers):
+    os.environ["NFB_LIB"] = _timers
 
 import torch
 
