@@ -25,6 +25,9 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <type_traits>
+#include <utility>
+
 #include "nfb_internal.h"
 #include "nfb_layout.h"
 #include "nfb_ptx.cuh"
@@ -36,7 +39,7 @@ namespace v6 {
 
 using Timer = PhaseTimer;
 
-constexpr int kNumSlots = 10;
+constexpr int kNumSlots = 9;
 constexpr int kSlotBytes = 16384;
 constexpr int kRowsMax = 512;  // sample rows of one pass of one stream
 #ifndef NFB_V6_HELPER
@@ -82,49 +85,111 @@ static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory li
 __host__ __device__ constexpr int num_halves(int s) { return step_info(s).nh1 > 0 ? 2 : 1; }
 __host__ __device__ constexpr int half_rows(int s, int h) { return h ? step_info(s).nh1 : step_info(s).nh0; }
 
-enum : uint32_t { kFromPe = 1u, kFirst = 2u, kLast = 4u };
-struct ProgEntry { uint32_t x, y, z, w; };  // x: idesc; y: A column (relative to P); z: flags; w: (src offset / 16) | rows << 20
-struct Group { uint16_t first, count; };
-constexpr int kMaxProg = 64, kMaxGroups = 20;
-struct ProgTable { ProgEntry e[kMaxProg]; Group g[kMaxGroups]; int n_entries, n_groups; };
-constexpr ProgTable make_prog() {
-  ProgTable t{};
-  int i = 0, g = 0;
+// The per-tile program.  A LOAD fills one ring slot: one [128 rows x 64 K] half-unit (16 KB), or — for the 16-row halves
+// (sigma row block of step 6, fc_rgb) — all K atoms of the half-step as 2 KB pieces, so that a slot is never spent on 2 KB.
+// 54 loads per tile pair = 6 rounds of the 9-slot ring: slot index, mbarrier parity and every shared-memory / TMEM operand
+// address of the MMA issue code are therefore COMPILE-TIME constants (the issue loop is fully unrolled; it was bounding the
+// tensor pipe at ~100 cycles per MMA when it read a constant-memory table and built descriptors at run time).
+struct Load {
+  int src[4];    // byte offset of each piece in the packed weight stream (nfb_layout.h)
+  int a_col[4];  // TMEM column (relative to P_x) of each piece's A operand; -1: the positional-encoding atom (A from shared memory)
+  int n_atoms;   // pieces = K atoms in this slot
+  int rows;      // MMA N = weight rows per piece (128 or 16)
+  int first, last, group;
+};
+constexpr int kMaxLoads = 56, kMaxGroups = 20;
+struct LoadTable { Load l[kMaxLoads]; int gfirst[kMaxGroups], gcount[kMaxGroups]; int n, n_groups, n_pieces; };
+constexpr LoadTable make_loads() {
+  LoadTable t{};
+  int i = 0, g = 0, pieces = 0;
   for (int s = 0; s < kNumSteps; ++s) {
     const StepInfo si = step_info(s);
     for (int h = 0; h < num_halves(s); ++h, ++g) {
-      t.g[g].first = (uint16_t)i;
-      t.g[g].count = (uint16_t)si.k_atoms;
       const int rows = half_rows(s, h);
-      for (int u = 0; u < si.k_atoms; ++u, ++i) {
-        uint32_t flags = 0;
-        if (si.pe_first && u == 0) flags |= kFromPe;
-        if (u == 0) flags |= kFirst;
-        if (u == si.k_atoms - 1) flags |= kLast;
-        t.e[i].x = umma_idesc_f16(kTileM, rows);
-        t.e[i].y = (uint32_t)(u - si.pe_first) * 32u;  // K atom a of the TMEM operand = P + 32 a (unused for the PE atom)
-        t.e[i].z = flags;
-        t.e[i].w = ((uint32_t)(step_offset_x1(s) + unit_offset_in_step(s, u) + h * si.nh0 * 128) >> 4) | ((uint32_t)rows << 20);
+      t.gfirst[g] = i;
+      if (rows == kTileM) {
+        for (int u = 0; u < si.k_atoms; ++u, ++i, ++pieces) {
+          Load& L = t.l[i];
+          L.n_atoms = 1; L.rows = rows; L.group = g;
+          L.src[0] = step_offset_x1(s) + unit_offset_in_step(s, u) + h * si.nh0 * 128;
+          L.a_col[0] = (si.pe_first && u == 0) ? -1 : (u - si.pe_first) * 32;
+          L.first = (u == 0); L.last = (u == si.k_atoms - 1);
+        }
+      } else {
+        Load& L = t.l[i];
+        L.n_atoms = si.k_atoms; L.rows = rows; L.group = g; L.first = 1; L.last = 1;
+        for (int u = 0; u < si.k_atoms; ++u, ++pieces) {
+          L.src[u] = step_offset_x1(s) + unit_offset_in_step(s, u) + h * si.nh0 * 128;
+          L.a_col[u] = u * 32;
+        }
+        ++i;
       }
+      t.gcount[g] = i - t.gfirst[g];
     }
   }
-  t.n_entries = i;
-  t.n_groups = g;
+  t.n = i; t.n_groups = g; t.n_pieces = pieces;
   return t;
 }
-constexpr ProgTable kProgHost = make_prog();
-static_assert(kProgHost.n_entries <= kMaxProg && kProgHost.n_groups <= kMaxGroups, "program table too small");
-constexpr int kNumGroups = kProgHost.n_groups;    // 17
-constexpr int last_pe_group() {  // the last half-step group whose first unit is the PE atom (step 3, half 1)
+constexpr LoadTable kLoads = make_loads();
+constexpr int kNumLoads = kLoads.n;          // 54
+constexpr int kNumGroups = kLoads.n_groups;  // 17
+static_assert(kNumLoads == 54 && kNumGroups == 17 && kLoads.n_pieces == 58, "program shape");
+static_assert(kNumLoads % kNumSlots == 0 && (kNumLoads / kNumSlots) % 2 == 0,
+              "every tile must start at ring slot 0 with the same mbarrier parity (static slot / parity in the issue code)");
+static_assert(kNumLoads % 2 == 0, "the multicast issuer alternates between the two CTAs per load");
+constexpr int last_pe_group() {  // the last half-step group whose first piece is the PE atom (step 3, half 1)
   int last = -1;
-  for (int g = 0; g < kProgHost.n_groups; ++g)
-    if (kProgHost.e[kProgHost.g[g].first].z & kFromPe) last = g;
+  for (int i = 0; i < kLoads.n; ++i)
+    if (kLoads.l[i].a_col[0] < 0) last = kLoads.l[i].group;
   return last;
 }
 constexpr int kLastPeGroup = last_pe_group();
 static_assert(kLastPeGroup == 7, "step 3, half 1");
-constexpr int kNumEntries = kProgHost.n_entries;  // 58
-__constant__ ProgTable c_prog = make_prog();
+__constant__ LoadTable c_loads = make_loads();  // the weight producer's copy (its loop is not unrolled)
+
+// ---- the MMA issue code of one stream, unrolled at compile time ----------------------------------------------------
+struct IssueCtx {
+  uint32_t smem_base, p_tmem, q_tmem, bar_full, bar_empty, bar_accfull;
+  uint64_t pe_desc;
+};
+template <int I>
+__device__ __forceinline__ void issue_load_mmas(const IssueCtx& c) {
+  constexpr Load L = kLoads.l[I];
+  constexpr int slot = I % kNumSlots;
+  constexpr uint32_t idesc = umma_idesc_f16(kTileM, L.rows);
+#pragma unroll
+  for (int a = 0; a < L.n_atoms; ++a) {
+    const uint64_t b_desc = umma_smem_desc_sw128(c.smem_base + kOffRing + slot * kSlotBytes + a * L.rows * 128);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t acc = (L.first && a == 0 && ks == 0) ? 0u : 1u;
+      if (L.a_col[a] < 0) umma_ss(c.q_tmem, c.pe_desc + (uint64_t)(ks * 2), b_desc + (uint64_t)(ks * 2), idesc, acc);
+      else umma_ts(c.q_tmem, c.p_tmem + (uint32_t)(L.a_col[a] + ks * 8), b_desc + (uint64_t)(ks * 2), idesc, acc);
+    }
+  }
+  umma_commit_multicast(c.bar_empty + slot * 8, (uint16_t)((1u << kCluster) - 1));  // this stream is done with the slot
+}
+// loads [I, I + N) of one group, kIssueUnits per elected block
+template <class F, int... G>
+__device__ __forceinline__ void for_each_group(F& f, std::integer_sequence<int, G...>) {
+  (f(std::integral_constant<int, G>{}), ...);
+}
+template <int I, int N>
+__device__ __forceinline__ void issue_loads(const IssueCtx& c) {
+  if constexpr (N > 0) {
+    constexpr bool two = (kIssueUnits == 2) && N >= 2;
+    mbar_wait(c.bar_full + (I % kNumSlots) * 8, (uint32_t)((I / kNumSlots) & 1));
+    if constexpr (two) mbar_wait(c.bar_full + ((I + 1) % kNumSlots) * 8, (uint32_t)(((I + 1) / kNumSlots) & 1));
+    tc_fence_after_sync();
+    if (elect_one()) {
+      issue_load_mmas<I>(c);
+      if constexpr (two) issue_load_mmas<I + 1>(c);
+      if constexpr (kLoads.l[I + (two ? 1 : 0)].last != 0) umma_commit(c.bar_accfull);
+    }
+    __syncwarp();
+    issue_loads<I + (two ? 2 : 1), N - (two ? 2 : 1)>(c);
+  }
+}
 
 // Accumulator chunk -> bias, ReLU, FP16: this thread's 64 columns of the half-step as 32 packed words.
 __device__ __forceinline__ void epi_load64(uint32_t t_q, uint32_t bias, uint32_t extra, uint32_t (&h)[32]) {
@@ -293,14 +358,16 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
       for (int t = 0; t < tiles_per_unit; ++t) {
         const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
         tm.lap(41);
-        for (int i = 0; i < kNumEntries; ++i) {
-          const uint32_t w = c_prog.e[i].w;
-          const uint32_t off = (w & 0xFFFFFu) << 4, bytes = (w >> 20) * 128u;
+        for (int i = 0; i < kNumLoads; ++i) {
+          const Load& L = c_loads.l[i];
+          const uint32_t piece = (uint32_t)L.rows * 128u, bytes = piece * (uint32_t)L.n_atoms;
           mbar_wait(bar_empty + slot * 8, phase ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
             if ((seq % kCluster) == cta_rank)
-              bulk_g2s_multicast(smem_base + kOffRing + slot * kSlotBytes, base + off, bytes, bar_full + slot * 8, kAllCtas);
+              for (int a = 0; a < L.n_atoms; ++a)
+                bulk_g2s_multicast(smem_base + kOffRing + slot * kSlotBytes + a * piece, base + L.src[a], piece, bar_full + slot * 8,
+                                   kAllCtas);
           }
           __syncwarp();
           ++seq;
@@ -311,11 +378,16 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
   } else if (warp == 1 || warp == 2) {
     // ============================== MMA issuer of stream x = warp - 1 ==============================
     const int x = warp - 1;
-    uint32_t sl = 0, ph = 0, ph_gate = 0;
-    const uint32_t p_tmem = tmem_base + (uint32_t)x * 256u;
-    const uint32_t q_tmem = p_tmem + 128u;
-    const uint64_t pe_desc = umma_smem_desc_sw128(smem_base + kOffPe + x * (kTileM * 128));
-    uint32_t ph_per = 0;
+    uint32_t ph_gate = 0, ph_per = 0;
+    IssueCtx c;
+    c.smem_base = smem_base;
+    c.p_tmem = tmem_base + (uint32_t)x * 256u;
+    c.q_tmem = c.p_tmem + 128u;
+    c.bar_full = bar_full;
+    c.bar_empty = bar_empty;
+    c.bar_accfull = bar_accfull + x * 8;
+    c.pe_desc = umma_smem_desc_sw128(smem_base + kOffPe + x * (kTileM * 128));
+    const uint32_t gate = bar_gate + x * 8;
     for (int it = 0; it < n_iter; ++it) {
       for (int t = 0; t < tiles_per_unit; ++t) {
         const bool fine_t = kHelper && t >= p.tiles_c;  // fine-pass tiles: PE buffer handshake with the helper warp
@@ -323,48 +395,21 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
           mbar_wait(bar_peready + x * 8, ph_per);
           ph_per ^= 1;
         }
-        for (int g = 0; g < kNumGroups; ++g) {
-          const uint32_t g_first = c_prog.g[g].first, g_count = c_prog.g[g].count;
-          mbar_wait(bar_gate + x * 8, ph_gate);  // operand P_x in place, accumulator Q_x read
+        // one half-step group: wait until operand P_x is in place and accumulator Q_x has been read, then its loads
+        auto group = [&](auto G) {
+          constexpr int g = decltype(G)::value;
+          mbar_wait(gate, ph_gate);
           ph_gate ^= 1;
           tc_fence_after_sync();
-          for (uint32_t j = 0; j < g_count; j += kIssueUnits) {
-            const bool two = (kIssueUnits == 2) && j + 1 < g_count;
-            const ProgEntry e0 = c_prog.e[g_first + j];
-            const ProgEntry e1 = c_prog.e[g_first + (two ? j + 1 : j)];
-            uint32_t sl1 = sl + 1, ph1 = ph;
-            if (sl1 == kNumSlots) { sl1 = 0; ph1 ^= 1; }
-            mbar_wait(bar_full + sl * 8, ph);
-            if (two) mbar_wait(bar_full + sl1 * 8, ph1);
-            tc_fence_after_sync();
-            const uint64_t b_desc0 = umma_smem_desc_sw128(smem_base + kOffRing + sl * kSlotBytes);
-            const uint64_t b_desc1 = umma_smem_desc_sw128(smem_base + kOffRing + sl1 * kSlotBytes);
-            if (elect_one()) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t bd = b_desc0 + (uint64_t)(ks * 2);
-                const uint32_t acc_flag = ((e0.z & kFirst) && ks == 0) ? 0u : 1u;
-                if (e0.z & kFromPe) umma_ss(q_tmem, pe_desc + (uint64_t)(ks * 2), bd, e0.x, acc_flag);
-                else umma_ts(q_tmem, p_tmem + e0.y + ks * 8, bd, e0.x, acc_flag);
-              }
-              umma_commit_multicast(bar_empty + sl * 8, kAllCtas);  // this stream is done with the slot
-              if (two) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_ts(q_tmem, p_tmem + e1.y + ks * 8, b_desc1 + (uint64_t)(ks * 2), e1.x, 1u);
-                umma_commit_multicast(bar_empty + sl1 * 8, kAllCtas);
-              }
-              if ((two ? e1.z : e0.z) & kLast) umma_commit(bar_accfull + x * 8);
+          issue_loads<kLoads.gfirst[g], kLoads.gcount[g]>(c);
+          if constexpr (g == kLastPeGroup) {  // step 3's second half issued: nothing reads PE buffer x after these MMAs
+            if (fine_t) {
+              if (elect_one()) umma_commit(bar_pefree + x * 8);
+              __syncwarp();
             }
-            __syncwarp();
-            if (two) { sl = sl1; ph = ph1; }
-            if (++sl == kNumSlots) { sl = 0; ph ^= 1; }
           }
-          if (fine_t && g == kLastPeGroup) {  // step 3's second half issued: nothing reads PE buffer x after these MMAs
-            if (elect_one()) umma_commit(bar_pefree + x * 8);
-            __syncwarp();
-          }
-        }
+        };
+        for_each_group(group, std::make_integer_sequence<int, kNumGroups>{});
       }
     }
   } else if (kHelper && warp == 3) {
@@ -805,15 +850,31 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
 
 }  // namespace v6
 
-int debug_prog_v6(int index, uint32_t* out) {  // host copy of the half-step program (tests): 4 words + group index
-  if (index < 0) return v6::kNumEntries;
-  if (index >= v6::kNumEntries) return -1;
-  const v6::ProgEntry& e = v6::kProgHost.e[index];
-  out[0] = e.x; out[1] = e.y; out[2] = e.z; out[3] = e.w;
-  int g = 0;
-  while (g + 1 < v6::kNumGroups && (int)v6::kProgHost.g[g + 1].first <= index) ++g;
-  out[4] = (uint32_t)g;
-  return 5;
+int debug_prog_v6(int index, uint32_t* out) {  // host copy of the two-tile program (tests), one entry per PIECE:
+  // idesc, A column (0xFFFFFFFF: PE atom), flags (1 from PE, 2 first / 4 last piece of its group), (src / 16) | rows << 20,
+  // group, load index, ring slot, byte offset inside the slot
+  constexpr v6::LoadTable t = v6::make_loads();
+  if (index < 0) return t.n_pieces;
+  if (index >= t.n_pieces) return -1;
+  int k = 0;
+  for (int i = 0; i < t.n; ++i) {
+    const v6::Load& L = t.l[i];
+    for (int a = 0; a < L.n_atoms; ++a, ++k) {
+      if (k != index) continue;
+      const bool g_first = (i == t.gfirst[L.group]) && a == 0;
+      const bool g_last = (i == t.gfirst[L.group] + t.gcount[L.group] - 1) && a == L.n_atoms - 1;
+      out[0] = umma_idesc_f16(kTileM, L.rows);
+      out[1] = (uint32_t)L.a_col[a];
+      out[2] = (L.a_col[a] < 0 ? 1u : 0u) | (g_first ? 2u : 0u) | (g_last ? 4u : 0u);
+      out[3] = ((uint32_t)L.src[a] >> 4) | ((uint32_t)L.rows << 20);
+      out[4] = (uint32_t)L.group;
+      out[5] = (uint32_t)i;
+      out[6] = (uint32_t)(i % v6::kNumSlots);
+      out[7] = (uint32_t)(a * L.rows * 128);
+      return 8;
+    }
+  }
+  return -1;
 }
 
 cudaError_t render2_kernel_setup() {

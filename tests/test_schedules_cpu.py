@@ -64,20 +64,33 @@ def test_one_tile_program_covers_the_weight_stream(lib):
 
 
 def test_two_tile_program_covers_the_weight_stream_in_half_units(lib):
+    """One entry per PIECE (a [rows x 64 K] block of the stream); pieces are grouped into LOADS, one ring slot each."""
     ents = entries(lib, 1)
     assert len(ents) == 58
     sp = spans(ents)
     assert_exact_cover(sp, STREAM_X1)                        # each half-unit once per tile pair
-    groups = {}
+    groups, loads = {}, {}
     for e, (off, nbytes) in zip(ents, sp):
         assert nbytes in (16384, 2048) and off % 16 == 0     # N = 128 or 16 rows of 128 bytes
         assert idesc_n(e[0]) * 128 == nbytes
         assert e[1] in (0, 32, 64, 96) or (e[2] & 1)         # K atom inside the 128-column operand region
         groups.setdefault(e[4], []).append(e)
+        loads.setdefault(e[5], []).append((e, nbytes))
     assert len(groups) == 17
     for g in groups.values():
-        assert g[0][2] & 2 and g[-1][2] & 4 and len(g) <= 5  # first / last flags; a group never exceeds half the 10-slot ring
+        assert g[0][2] & 2 and g[-1][2] & 4                  # first / last flags
         assert all(not (e[2] & 2) for e in g[1:]) and all(not (e[2] & 4) for e in g[:-1])
+        assert len({e[5] for e in g}) <= 5                   # a group never needs more than 5 of the 9 ring slots at once
+    # static ring: 54 loads = 6 full rounds of 9 slots, so every tile starts at slot 0 with the same mbarrier parity
+    assert sorted(loads) == list(range(54))
+    for i, pieces in loads.items():
+        assert all(e[6] == i % 9 for e, _ in pieces)
+        pos = 0
+        for e, nbytes in pieces:                             # pieces are packed back to back, 1024-byte (swizzle) aligned
+            assert e[7] == pos and pos % 1024 == 0
+            pos += nbytes
+        assert pos <= 16384
+        assert len({e[4] for e, _ in pieces}) == 1           # a load never straddles two half-step groups
 
 
 def test_backward_chain_program(lib):
