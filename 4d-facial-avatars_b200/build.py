@@ -1,7 +1,7 @@
 """Build lib/libnfb.so (the C-ABI shared library of include/nfb.h) in-tree with nvcc for sm_100a.
 
 The .so is git-ignored but travels to the GPU box with the repo snapshot.  Rebuilds only when a
-source is newer than the library.  Usage: python 4d-facial-avatars_b200/build.py [--force] [--verbose] [--timers]
+source is newer than the library.  Usage: python 4d-facial-avatars_b200/build.py [--force] [--verbose] [--timers] | --variant NAME -D... (experiment build lib/libnfb_NAME.so)
 
 --timers additionally builds lib/libnfb_timers.so with the phase timers compiled in (-DNFB_TIMERS=1; they cost registers in
 the kernels' hot loops, so the product library does not carry them); tools/phase_profile.py loads it through NFB_LIB.
@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libnfb.so")
-SOURCES = ["nfb_api.cu", "nfb_pack.cu", "nfb_render.cu", "nfb_render2.cu", "nfb_train.cu"]
-HEADERS = ["nfb_internal.h", "nfb_layout.h", "nfb_ptx.cuh", "nfb_save.cuh", "nfb_render_common.cuh", os.path.join("..", "..", "include", "nfb.h")]
+SOURCES = ["nfb_api.cu", "nfb_pack.cu", "nfb_render.cu", "nfb_render2.cu", "nfb_render3.cu", "nfb_train.cu"]
+HEADERS = ["nfb_internal.h", "nfb_layout.h", "nfb_ptx.cuh", "nfb_save.cuh", "nfb_render_common.cuh", "nfb_tile2.cuh", os.path.join("..", "..", "include", "nfb.h")]
 
 
 def _nvcc():
@@ -33,14 +33,17 @@ def needs_build():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, timers=False):
+def build(force=False, verbose=False, timers=False, variant=None, defines=()):
+    """variant + defines: an experiment build lib/libnfb_<variant>.so with extra -D flags (select it with NFB_LIB)."""
     out = os.path.join(LIB_DIR, "libnfb_timers.so") if timers else LIB
-    if not timers and not force and not needs_build():
+    if variant:
+        out = os.path.join(LIB_DIR, f"libnfb_{variant}.so")
+    if not timers and not variant and not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-DNFB_BUILD"] + (["-DNFB_TIMERS=1"] if timers else []) + ["-o", out] + srcs
+           "-Xcompiler", "-fPIC", "-shared", "-DNFB_BUILD"] + (["-DNFB_TIMERS=1"] if timers else []) + list(defines) + ["-o", out] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -53,6 +56,10 @@ def build(force=False, verbose=False, timers=False):
 
 
 if __name__ == "__main__":
+    if "--variant" in sys.argv:  # python build.py --variant NAME -DFOO=1 [-DBAR=2 ...] [--timers]
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        print(build(verbose="--verbose" in sys.argv, timers=False, variant=name, defines=[a for a in sys.argv if a.startswith("-D")]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
     if "--timers" in sys.argv:
         print(build(verbose="--verbose" in sys.argv, timers=True))

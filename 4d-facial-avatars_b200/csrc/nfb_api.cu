@@ -36,6 +36,7 @@ struct NfbHandle {
   nfb::NetBuffers net[2];
   bool frame_set = false;
   bool use_render2 = true;
+  bool use_render3 = true;
   bool train_render2 = false;
   long long launches = 0;
   // cached torch.linspace(0,1,n) tables on the device
@@ -134,9 +135,11 @@ int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
   NFB_CUDA(dev_alloc(&h->d_latent, nfb::kDimLatent));
   NFB_CUDA(nfb::render_kernel_setup());
   NFB_CUDA(nfb::render2_kernel_setup());
+  NFB_CUDA(nfb::render3_kernel_setup());
   {  // NFB_KERNEL=v4 forces the one-tile-in-flight kernel everywhere (default: the two-tile kernel where it applies)
     const char* k = std::getenv("NFB_KERNEL");
     h->use_render2 = !(k && std::strcmp(k, "v4") == 0);
+    h->use_render3 = h->use_render2 && !(k && std::strcmp(k, "v6") == 0);  // NFB_KERNEL=v6: two tiles in flight, passes not pipelined
     // The training forward defaults to the one-tile kernel: with the record stores the two-tile kernel's row warps spill
     // (216 B) and it is slower there (measured 1.46 ms vs 1.01 ms per 2048-ray forward); NFB_TRAIN_KERNEL=v6 selects it.
     const char* tk = std::getenv("NFB_TRAIN_KERNEL");
@@ -292,7 +295,8 @@ static int render_impl(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm,
   // fast-mode evaluation runs the two-tiles-in-flight kernel (the training forward only on request, see nfb_create); exact
   // mode (hi+lo operands need twice the TMEM columns) and the layer probe run the one-tile kernel
   const bool two_tile = h->use_render2 && !exact && !p.dbg_act && (!train || h->train_render2);
-  if (two_tile) NFB_CUDA(nfb::launch_render2(p, h->num_sms, st, &h->launches));
+  if (two_tile && !train && h->use_render3 && nfb::render3_supports(p)) NFB_CUDA(nfb::launch_render3(p, h->num_sms, st, &h->launches));
+  else if (two_tile) NFB_CUDA(nfb::launch_render2(p, h->num_sms, st, &h->launches));
   else NFB_CUDA(nfb::launch_render(p, exact ? 1 : 0, h->num_sms, st, &h->launches));
   if (train) h->tr.valid = true;
   return NFB_OK;

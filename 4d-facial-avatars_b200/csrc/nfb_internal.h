@@ -107,5 +107,10 @@ cudaError_t render_kernel_setup();  // opt-in to the large dynamic shared memory
 // Two-tiles-in-flight kernel (nfb_render2.cu): fast mode, evaluation (no training records, no layer probe / phase timers).
 cudaError_t render2_kernel_setup();
 cudaError_t launch_render2(const RenderParams& p, int num_sms, cudaStream_t st, long long* launches);
+// Two tiles in flight + software-pipelined passes (nfb_render3.cu): fast-mode evaluation of the configurations its fixed
+// shared-memory budget covers (render3_supports), bit-identical to nfb_render2.cu.
+cudaError_t render3_kernel_setup();
+bool render3_supports(const RenderParams& p);
+cudaError_t launch_render3(const RenderParams& p, int num_sms, cudaStream_t st, long long* launches);
 
 }  // namespace nfb

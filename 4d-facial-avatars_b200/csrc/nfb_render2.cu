@@ -33,14 +33,15 @@
 #include "nfb_ptx.cuh"
 #include "nfb_render_common.cuh"
 #include "nfb_save.cuh"
+#include "nfb_tile2.cuh"
 
 namespace nfb {
 namespace v6 {
 
+using namespace t2;
+
 using Timer = PhaseTimer;
 
-constexpr int kNumSlots = 9;
-constexpr int kSlotBytes = 16384;
 constexpr int kRowsMax = 512;  // sample rows of one pass of one stream
 #ifndef NFB_V6_HELPER
 #define NFB_V6_HELPER 1
@@ -48,15 +49,10 @@ constexpr int kRowsMax = 512;  // sample rows of one pass of one stream
 // Warp 3 (otherwise idle) computes the positional encoding of the NEXT fine-pass tile of both streams while the row warps
 // run the current tile's epilogues; with 0 the row warps do it themselves after step 3 (tensor core idle meanwhile).
 constexpr bool kHelper = NFB_V6_HELPER != 0;
-constexpr int kIssueUnits = 2;  // weight units (4 MMAs each) per elected MMA block; 1 and 4 measured slower
 // Warps: 0 = weight producer, 1 / 2 = MMA issuer of stream X / Y (different SM sub-partitions; one warp issuing both streams
 // in turn measured 4.37 M rays/s against 4.51 M), 3 = idle, 4..11 = row warps.  12 warps still allow 168 registers per thread.
 constexpr int kRowWarp0 = 4;
 constexpr int kThreads = (kRowWarp0 + 8) * 32;
-#ifndef NFB_V6_CLUSTER
-#define NFB_V6_CLUSTER 2
-#endif
-constexpr int kCluster = NFB_V6_CLUSTER;  // CTAs sharing every weight half-unit through one multicast L2 read
 constexpr int kRowThreads = 256;
 constexpr uint32_t kRowBarrier = 1;
 
@@ -80,150 +76,6 @@ constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
-
-// Half-steps.  Step s (nfb_layout.h) has 1 or 2 halves; half h covers weight rows [h * nh0, h * nh0 + N_h).
-__host__ __device__ constexpr int num_halves(int s) { return step_info(s).nh1 > 0 ? 2 : 1; }
-__host__ __device__ constexpr int half_rows(int s, int h) { return h ? step_info(s).nh1 : step_info(s).nh0; }
-
-// The per-tile program.  A LOAD fills one ring slot: one [128 rows x 64 K] half-unit (16 KB), or — for the 16-row halves
-// (sigma row block of step 6, fc_rgb) — all K atoms of the half-step as 2 KB pieces, so that a slot is never spent on 2 KB.
-// 54 loads per tile pair = 6 rounds of the 9-slot ring: slot index, mbarrier parity and every shared-memory / TMEM operand
-// address of the MMA issue code are therefore COMPILE-TIME constants (the issue loop is fully unrolled; it was bounding the
-// tensor pipe at ~100 cycles per MMA when it read a constant-memory table and built descriptors at run time).
-struct Load {
-  int src[4];    // byte offset of each piece in the packed weight stream (nfb_layout.h)
-  int a_col[4];  // TMEM column (relative to P_x) of each piece's A operand; -1: the positional-encoding atom (A from shared memory)
-  int n_atoms;   // pieces = K atoms in this slot
-  int rows;      // MMA N = weight rows per piece (128 or 16)
-  int first, last, group;
-};
-constexpr int kMaxLoads = 56, kMaxGroups = 20;
-struct LoadTable { Load l[kMaxLoads]; int gfirst[kMaxGroups], gcount[kMaxGroups]; int n, n_groups, n_pieces; };
-constexpr LoadTable make_loads() {
-  LoadTable t{};
-  int i = 0, g = 0, pieces = 0;
-  for (int s = 0; s < kNumSteps; ++s) {
-    const StepInfo si = step_info(s);
-    for (int h = 0; h < num_halves(s); ++h, ++g) {
-      const int rows = half_rows(s, h);
-      t.gfirst[g] = i;
-      if (rows == kTileM) {
-        for (int u = 0; u < si.k_atoms; ++u, ++i, ++pieces) {
-          Load& L = t.l[i];
-          L.n_atoms = 1; L.rows = rows; L.group = g;
-          L.src[0] = step_offset_x1(s) + unit_offset_in_step(s, u) + h * si.nh0 * 128;
-          L.a_col[0] = (si.pe_first && u == 0) ? -1 : (u - si.pe_first) * 32;
-          L.first = (u == 0); L.last = (u == si.k_atoms - 1);
-        }
-      } else {
-        Load& L = t.l[i];
-        L.n_atoms = si.k_atoms; L.rows = rows; L.group = g; L.first = 1; L.last = 1;
-        for (int u = 0; u < si.k_atoms; ++u, ++pieces) {
-          L.src[u] = step_offset_x1(s) + unit_offset_in_step(s, u) + h * si.nh0 * 128;
-          L.a_col[u] = u * 32;
-        }
-        ++i;
-      }
-      t.gcount[g] = i - t.gfirst[g];
-    }
-  }
-  t.n = i; t.n_groups = g; t.n_pieces = pieces;
-  return t;
-}
-constexpr LoadTable kLoads = make_loads();
-constexpr int kNumLoads = kLoads.n;          // 54
-constexpr int kNumGroups = kLoads.n_groups;  // 17
-static_assert(kNumLoads == 54 && kNumGroups == 17 && kLoads.n_pieces == 58, "program shape");
-static_assert(kNumLoads % kNumSlots == 0 && (kNumLoads / kNumSlots) % 2 == 0,
-              "every tile must start at ring slot 0 with the same mbarrier parity (static slot / parity in the issue code)");
-static_assert(kNumLoads % 2 == 0, "the multicast issuer alternates between the two CTAs per load");
-constexpr int last_pe_group() {  // the last half-step group whose first piece is the PE atom (step 3, half 1)
-  int last = -1;
-  for (int i = 0; i < kLoads.n; ++i)
-    if (kLoads.l[i].a_col[0] < 0) last = kLoads.l[i].group;
-  return last;
-}
-constexpr int kLastPeGroup = last_pe_group();
-static_assert(kLastPeGroup == 7, "step 3, half 1");
-__constant__ LoadTable c_loads = make_loads();  // the weight producer's copy (its loop is not unrolled)
-
-// ---- the MMA issue code of one stream, unrolled at compile time ----------------------------------------------------
-struct IssueCtx {
-  uint32_t smem_base, p_tmem, q_tmem, bar_full, bar_empty, bar_accfull;
-  uint64_t pe_desc;
-};
-template <int I>
-__device__ __forceinline__ void issue_load_mmas(const IssueCtx& c) {
-  constexpr Load L = kLoads.l[I];
-  constexpr int slot = I % kNumSlots;
-  constexpr uint32_t idesc = umma_idesc_f16(kTileM, L.rows);
-#pragma unroll
-  for (int a = 0; a < L.n_atoms; ++a) {
-    const uint64_t b_desc = umma_smem_desc_sw128(c.smem_base + kOffRing + slot * kSlotBytes + a * L.rows * 128);
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint32_t acc = (L.first && a == 0 && ks == 0) ? 0u : 1u;
-      if (L.a_col[a] < 0) umma_ss(c.q_tmem, c.pe_desc + (uint64_t)(ks * 2), b_desc + (uint64_t)(ks * 2), idesc, acc);
-      else umma_ts(c.q_tmem, c.p_tmem + (uint32_t)(L.a_col[a] + ks * 8), b_desc + (uint64_t)(ks * 2), idesc, acc);
-    }
-  }
-  umma_commit_multicast(c.bar_empty + slot * 8, (uint16_t)((1u << kCluster) - 1));  // this stream is done with the slot
-}
-// loads [I, I + N) of one group, kIssueUnits per elected block
-template <class F, int... G>
-__device__ __forceinline__ void for_each_group(F& f, std::integer_sequence<int, G...>) {
-  (f(std::integral_constant<int, G>{}), ...);
-}
-template <int I, int N>
-__device__ __forceinline__ void issue_loads(const IssueCtx& c) {
-  if constexpr (N > 0) {
-    constexpr bool two = (kIssueUnits == 2) && N >= 2;
-    mbar_wait(c.bar_full + (I % kNumSlots) * 8, (uint32_t)((I / kNumSlots) & 1));
-    if constexpr (two) mbar_wait(c.bar_full + ((I + 1) % kNumSlots) * 8, (uint32_t)(((I + 1) / kNumSlots) & 1));
-    tc_fence_after_sync();
-    if (elect_one()) {
-      issue_load_mmas<I>(c);
-      if constexpr (two) issue_load_mmas<I + 1>(c);
-      if constexpr (kLoads.l[I + (two ? 1 : 0)].last != 0) umma_commit(c.bar_accfull);
-    }
-    __syncwarp();
-    issue_loads<I + (two ? 2 : 1), N - (two ? 2 : 1)>(c);
-  }
-}
-
-// Accumulator chunk -> bias, ReLU, FP16: this thread's 64 columns of the half-step as 32 packed words.
-__device__ __forceinline__ void epi_load64(uint32_t t_q, uint32_t bias, uint32_t extra, uint32_t (&h)[32]) {
-  uint32_t va[32], vb[32], ha[16], hb[16], lo[16];
-  tmem_ld32(t_q, va);
-  tmem_ld32(t_q + 32, vb);
-  tmem_wait_ld();
-  epi_math<false>(va, bias, extra, nullptr, ha, lo);
-  epi_math<false>(vb, bias + 128, extra ? extra + 128 : 0u, nullptr, hb, lo);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) { h[j] = ha[j]; h[16 + j] = hb[j]; }
-}
-// Half-0 variant: the result stays in registers, so the accumulator is free as soon as it has been LOADED — the gate
-// (`bar`, one arrival per warp) is signalled before the arithmetic, which then overlaps the next half-step's MMAs.
-__device__ __forceinline__ void epi_load64_early(uint32_t t_q, uint32_t bias, uint32_t extra, uint32_t (&h)[32], uint32_t bar, int lane) {
-  uint32_t va[32], vb[32], ha[16], hb[16], lo[16];
-  tmem_ld32(t_q, va);
-  tmem_ld32(t_q + 32, vb);
-  tmem_wait_ld();
-  tc_fence_before_sync();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(bar);
-  epi_math<false>(va, bias, extra, nullptr, ha, lo);
-  epi_math<false>(vb, bias + 128, extra ? extra + 128 : 0u, nullptr, hb, lo);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) { h[j] = ha[j]; h[16 + j] = hb[j]; }
-}
-__device__ __forceinline__ void store32(uint32_t t_p, const uint32_t (&h)[32]) {
-  uint32_t a[16], b[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) { a[j] = h[j]; b[j] = h[16 + j]; }
-  tmem_st16(t_p, a);
-  tmem_st16(t_p + 16, b);
-}
 
 // Sample depth + positional encoding of tile t of stream x -> PE buffer x (63 lanes + zero pad, FP16, swizzled).
 __device__ __forceinline__ void prologue_fn(const RenderParams& p, const RayP* __restrict__ rayp, float* __restrict__ carry_z,
@@ -358,21 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
       for (int t = 0; t < tiles_per_unit; ++t) {
         const uint8_t* base = p.wstream[t < p.tiles_c ? 0 : 1];
         tm.lap(41);
-        for (int i = 0; i < kNumLoads; ++i) {
-          const Load& L = c_loads.l[i];
-          const uint32_t piece = (uint32_t)L.rows * 128u, bytes = piece * (uint32_t)L.n_atoms;
-          mbar_wait(bar_empty + slot * 8, phase ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(bar_full + slot * 8, bytes);
-            if ((seq % kCluster) == cta_rank)
-              for (int a = 0; a < L.n_atoms; ++a)
-                bulk_g2s_multicast(smem_base + kOffRing + slot * kSlotBytes + a * piece, base + L.src[a], piece, bar_full + slot * 8,
-                                   kAllCtas);
-          }
-          __syncwarp();
-          ++seq;
-          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
-        }
+        produce_tile(base, smem_base + kOffRing, bar_full, bar_empty, cta_rank, slot, phase, seq);
       }
     }
   } else if (warp == 1 || warp == 2) {
@@ -380,7 +218,8 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
     const int x = warp - 1;
     uint32_t ph_gate = 0, ph_per = 0;
     IssueCtx c;
-    c.smem_base = smem_base;
+    c.ring = smem_base + kOffRing;
+    c.ring_desc_lo = desc_lo_of(smem_base + kOffRing);
     c.p_tmem = tmem_base + (uint32_t)x * 256u;
     c.q_tmem = c.p_tmem + 128u;
     c.bar_full = bar_full;
@@ -853,12 +692,12 @@ __global__ void __launch_bounds__(kThreads, 1) render2_kernel(const __grid_const
 int debug_prog_v6(int index, uint32_t* out) {  // host copy of the two-tile program (tests), one entry per PIECE:
   // idesc, A column (0xFFFFFFFF: PE atom), flags (1 from PE, 2 first / 4 last piece of its group), (src / 16) | rows << 20,
   // group, load index, ring slot, byte offset inside the slot
-  constexpr v6::LoadTable t = v6::make_loads();
+  constexpr t2::LoadTable t = t2::make_loads();
   if (index < 0) return t.n_pieces;
   if (index >= t.n_pieces) return -1;
   int k = 0;
   for (int i = 0; i < t.n; ++i) {
-    const v6::Load& L = t.l[i];
+    const t2::Load& L = t.l[i];
     for (int a = 0; a < L.n_atoms; ++a, ++k) {
       if (k != index) continue;
       const bool g_first = (i == t.gfirst[L.group]) && a == 0;
@@ -869,7 +708,7 @@ int debug_prog_v6(int index, uint32_t* out) {  // host copy of the two-tile prog
       out[3] = ((uint32_t)L.src[a] >> 4) | ((uint32_t)L.rows << 20);
       out[4] = (uint32_t)L.group;
       out[5] = (uint32_t)i;
-      out[6] = (uint32_t)(i % v6::kNumSlots);
+      out[6] = (uint32_t)(i % t2::kNumSlots);
       out[7] = (uint32_t)(a * L.rows * 128);
       return 8;
     }
