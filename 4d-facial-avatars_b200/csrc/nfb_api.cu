@@ -53,6 +53,7 @@ struct NfbHandle {
     size_t cap_zc = 0, cap_rawc = 0, cap_zf = 0, cap_rawf = 0, cap_dn = 0;
     float* acc[2] = {nullptr, nullptr};                 // kAccFloats each
     float* scal = nullptr;                              // [0] scale, [1] 1/scale, [2] max |d raw| (bits)
+    float* cond = nullptr;                              // [108] conditioning vector of the frame the forward rendered
     int n_rays = 0, nc = 0, nf = 0, rays_per_unit = 0, tiles_c = 0, tiles_f = 0, n_units = 0, has_bg = 0, white_bkgd = 0;
     bool valid = false;
   } tr;
@@ -118,8 +119,6 @@ int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
     nfb::NetBuffers& nb = h->net[n];
     NFB_CUDA(dev_alloc(&nb.stream_x1, nfb::kStreamBytesX1));
     NFB_CUDA(dev_alloc(&nb.stream_x3, nfb::kStreamBytesX3));
-    NFB_CUDA(dev_alloc(&nb.w6, 144 * 256));
-    NFB_CUDA(dev_alloc(&nb.b6, 144));
     NFB_CUDA(dev_alloc(&nb.bias_static, nfb::kBiasFloats));
     NFB_CUDA(dev_alloc(&nb.bias_frame, nfb::kBiasFloats));
     NFB_CUDA(dev_alloc(&nb.w0c, 256 * nfb::kDimCond));
@@ -129,6 +128,7 @@ int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
     NFB_CUDA(dev_alloc(&h->tr.acc[n], nfb::kAccFloats));
   }
   NFB_CUDA(dev_alloc(&h->tr.scal, 4));
+  NFB_CUDA(dev_alloc(&h->tr.cond, nfb::kDimCond));
   NFB_CUDA(dev_alloc(&h->cond, nfb::kDimCond));
   NFB_CUDA(nfb::train_kernels_setup());
   NFB_CUDA(dev_alloc(&h->d_expr, nfb::kDimExpr));
@@ -154,12 +154,12 @@ int nfb_destroy(NfbHandle* h) {
   cudaSetDevice(h->device);
   for (int n = 0; n < 2; ++n) {
     nfb::NetBuffers& nb = h->net[n];
-    cudaFree(nb.stream_x1); cudaFree(nb.stream_x3); cudaFree(nb.w6); cudaFree(nb.b6); cudaFree(nb.bias_static);
+    cudaFree(nb.stream_x1); cudaFree(nb.stream_x3); cudaFree(nb.bias_static);
     cudaFree(nb.bias_frame); cudaFree(nb.w0c); cudaFree(nb.w3c); cudaFree(nb.wd0b_t); cudaFree(nb.stream_bwd);
     cudaFree(h->tr.acc[n]);
   }
   cudaFree(h->tr.rec); cudaFree(h->tr.draw); cudaFree(h->tr.z_c); cudaFree(h->tr.raw_c); cudaFree(h->tr.z_f); cudaFree(h->tr.raw_f);
-  cudaFree(h->tr.dnorm); cudaFree(h->tr.scal); cudaFree(h->cond);
+  cudaFree(h->tr.dnorm); cudaFree(h->tr.scal); cudaFree(h->tr.cond); cudaFree(h->cond);
   cudaFree(h->lin_c); cudaFree(h->lin_f); cudaFree(h->d_expr); cudaFree(h->d_latent); cudaFree(h->d_bg); cudaFree(h->d_out);
   delete h;
   return NFB_OK;
@@ -172,10 +172,46 @@ int nfb_load_weights(NfbHandle* h, int which, const float* const params[26], voi
   NFB_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   nfb::NetBuffers& nb = h->net[which];
-  NFB_CUDA(nfb::launch_load_weights(nb, params, st, &h->launches));
-  NFB_CUDA(nfb::launch_pack_bwd(nb, params, st, &h->launches));  // transposed stream for the backward chain
+  nfb::NetBuffers* const nbs[2] = {&nb, nullptr};
+  const float* const* const ps[2] = {params, nullptr};
+  NFB_CUDA(nfb::launch_repack(nbs, ps, 1, st, &h->launches));  // forward streams, transposed backward stream, bias / column blocks
   nb.loaded = true;
   h->frame_set = false;  // folded biases are stale
+  return NFB_OK;
+}
+
+int nfb_repack(NfbHandle* h, const float* const params_coarse[26], const float* const params_fine[26], void* stream) {
+  if (!h || !params_coarse) return NFB_ERR_INVALID;
+  for (int i = 0; i < 26; ++i)
+    if (!params_coarse[i] || (params_fine && !params_fine[i])) return NFB_ERR_INVALID;
+  NFB_CUDA(cudaSetDevice(h->device));
+  nfb::NetBuffers* const nbs[2] = {&h->net[0], &h->net[1]};
+  const float* const* const ps[2] = {params_coarse, params_fine};
+  NFB_CUDA(nfb::launch_repack(nbs, ps, params_fine ? 2 : 1, static_cast<cudaStream_t>(stream), &h->launches));
+  h->net[0].loaded = true;
+  if (params_fine) h->net[1].loaded = true;
+  h->frame_set = false;  // folded biases are stale
+  return NFB_OK;
+}
+
+int nfb_loss_mse_grad(NfbHandle* h, const float* rgb_coarse, const float* rgb_fine, const float* target, int n_rays,
+                      long long n_total, float* grad_rgb_coarse, float* grad_rgb_fine, float* loss, void* stream) {
+  if (!h || !rgb_coarse || !target || !grad_rgb_coarse || !loss || n_rays < 0 || n_total < n_rays || n_total <= 0) return NFB_ERR_INVALID;
+  if (rgb_fine && !grad_rgb_fine) return NFB_ERR_INVALID;
+  NFB_CUDA(cudaSetDevice(h->device));
+  NFB_CUDA(nfb::launch_loss_grad(rgb_coarse, rgb_fine, target, n_rays, n_total, grad_rgb_coarse, grad_rgb_fine, loss,
+                                 static_cast<cudaStream_t>(stream), &h->launches));
+  return NFB_OK;
+}
+
+int nfb_adam_step(NfbHandle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, const NfbAdam* hp,
+                  void* stream) {
+  if (!h || !params || !grads || !exp_avg || !exp_avg_sq || !hp || n <= 0 || hp->step < 1) return NFB_ERR_INVALID;
+  // the regularised row must not straddle two 256-float chunks (one thread block each): its norm is taken per block
+  if (hp->reg_offset >= 0 && (hp->reg_offset + nfb::kDimLatent > n || hp->reg_offset % nfb::kDimLatent != 0)) return NFB_ERR_INVALID;
+  NFB_CUDA(cudaSetDevice(h->device));
+  NFB_CUDA(nfb::launch_adam(params, grads, exp_avg, exp_avg_sq, n, hp->lr, hp->beta1, hp->beta2, hp->eps, hp->step, hp->grad_scale,
+                            hp->reg_offset, hp->reg_weight, static_cast<cudaStream_t>(stream), &h->launches));
   return NFB_OK;
 }
 
@@ -184,9 +220,8 @@ int nfb_set_frame(NfbHandle* h, const float* expression, const float* latent, vo
   if (!h->net[0].loaded) return NFB_ERR_STATE;
   NFB_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (int n = 0; n < 2; ++n)
-    if (h->net[n].loaded) NFB_CUDA(nfb::launch_frame_fold(h->net[n], expression, latent, st, &h->launches));
-  NFB_CUDA(nfb::launch_cond(expression, latent, h->cond, st, &h->launches));
+  nfb::NetBuffers* const nbs[2] = {&h->net[0], &h->net[1]};
+  NFB_CUDA(nfb::launch_frame_fold(nbs, h->net[1].loaded ? 2 : 1, expression, latent, h->cond, st, &h->launches));
   h->frame_set = true;
   return NFB_OK;
 }
@@ -287,6 +322,8 @@ static int render_impl(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm,
       if ((rc = ensure_cap(&tr.z_f, &tr.cap_zf, n * (nc + nf)))) return rc;
       if ((rc = ensure_cap(&tr.raw_f, &tr.cap_rawf, n * (nc + nf) * 4))) return rc;
     }
+    // a later nfb_set_frame (e.g. a validation render before the backward) must not change what the backward differentiates
+    NFB_CUDA(cudaMemcpyAsync(tr.cond, h->cond, nfb::kDimCond * sizeof(float), cudaMemcpyDeviceToDevice, st));
     p.save_rec = tr.rec; p.save_dnorm = tr.dnorm; p.save_raw_c = tr.raw_c; p.save_raw_f = tr.raw_f;
     p.dbg_z_c = tr.z_c; p.dbg_z_f = tr.z_f;
     tr.n_rays = rays->n_rays; tr.nc = nc; tr.nf = nf; tr.rays_per_unit = p.rays_per_unit; tr.tiles_c = p.tiles_c;
@@ -356,7 +393,7 @@ int nfb_render_backward(NfbHandle* h, const NfbOutGrads* og, const float* const 
     d.t_base = net ? tr.tiles_c : 0; d.t_cnt = net ? tr.tiles_f : tr.tiles_c;
     d.acc = tr.acc[net]; d.scal = tr.scal;
     NFB_CUDA(nfb::launch_dw(d, h->num_sms, st, &h->launches));
-    NFB_CUDA(nfb::launch_finalize(net ? params_fine : params_coarse, net ? grads_fine : grads_coarse, tr.acc[net], h->cond, st,
+    NFB_CUDA(nfb::launch_finalize(net ? params_fine : params_coarse, net ? grads_fine : grads_coarse, tr.acc[net], tr.cond, st,
                                   &h->launches));
   }
   if (grad_latent)

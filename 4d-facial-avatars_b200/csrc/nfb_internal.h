@@ -10,8 +10,6 @@ namespace nfb {
 struct NetBuffers {
   uint8_t* stream_x1 = nullptr;  // kStreamBytesX1: FP16 weights, swizzled units in execution order
   uint8_t* stream_x3 = nullptr;  // kStreamBytesX3: hi unit, lo unit, ...
-  float* w6 = nullptr;           // [144,256] folded layers_dir.0 / fc_alpha
-  float* b6 = nullptr;           // [144]
   float* bias_static = nullptr;  // [kBiasFloats]
   float* bias_frame = nullptr;   // [kBiasFloats] bias_static + per-frame fold (what the kernel reads)
   float* w0c = nullptr;          // [256,108] conditioning columns of layers_xyz.0
@@ -89,8 +87,6 @@ int debug_prog_v6(int index, uint32_t* out);
 int debug_prog_chain(int index, uint32_t* out);
 int debug_jobs_dw(int index, uint32_t* out);
 cudaError_t train_kernels_setup();
-cudaError_t launch_pack_bwd(NetBuffers& nb, const float* const params[26], cudaStream_t st, long long* launches);
-cudaError_t launch_cond(const float* expr, const float* latent, float* cond, cudaStream_t st, long long* launches);
 cudaError_t launch_composite_bwd(const CompBwdParams& q, float* scal, cudaStream_t st, long long* launches);
 cudaError_t launch_chain(const ChainParams& p, int num_sms, cudaStream_t st, long long* launches);
 cudaError_t launch_dw(const DwParams& p, int num_sms, cudaStream_t st, long long* launches);
@@ -99,8 +95,17 @@ cudaError_t launch_finalize(const float* const params[26], float* const grads[26
 cudaError_t launch_latent_grad(const float* const params_c[26], const float* const params_f[26], const float* acc_c,
                                const float* acc_f, float* out, cudaStream_t st, long long* launches);
 
-cudaError_t launch_load_weights(NetBuffers& nb, const float* const params[26], cudaStream_t st, long long* launches);
-cudaError_t launch_frame_fold(NetBuffers& nb, const float* expr, const float* latent, cudaStream_t st, long long* launches);
+// One launch: FP32 parameters of n_nets (1 or 2) networks -> forward / backward weight streams, bias block, conditioning and
+// direction columns (nfb_pack.cu: repack_kernel).
+cudaError_t launch_repack(NetBuffers* const nb[2], const float* const* const params[2], int n_nets, cudaStream_t st, long long* launches);
+// One launch: per-frame bias fold of the loaded networks + cond[108] = [expr / 3 ; latent].
+cudaError_t launch_frame_fold(NetBuffers* const nb[2], int n_nets, const float* expr, const float* latent, float* cond,
+                              cudaStream_t st, long long* launches);
+// Training-step tail (nfb_optim.cu): d mse / d rgb (+ loss sums), Adam over a flat bucket with zero_grad fused.
+cudaError_t launch_loss_grad(const float* rgb_c, const float* rgb_f, const float* target, int n_rays, long long n_total, float* g_c,
+                             float* g_f, float* loss, cudaStream_t st, long long* launches);
+cudaError_t launch_adam(float* p, float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
+                        float grad_scale, long long reg_off, float reg_w, cudaStream_t st, long long* launches);
 // precision: 0 = fast (x1), 1 = exact (x3).  num_sms = CTAs to launch at most.
 cudaError_t launch_render(const RenderParams& p, int precision, int num_sms, cudaStream_t st, long long* launches);
 cudaError_t render_kernel_setup();  // opt-in to the large dynamic shared memory size

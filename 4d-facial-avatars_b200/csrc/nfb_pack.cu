@@ -1,8 +1,8 @@
-// nfb_pack.cu — load-time and per-frame preparation kernels (not on the per-ray hot path):
-//   * fold_feat_kernel : fc_feat pre-multiplied into fc_alpha and layers_dir.0[:, :256]  (FP64 accumulate)
-//   * pack_step_kernel : FP32 weights -> FP16 hi/lo, written as the swizzled shared-memory image
-//                        (nfb_layout.h) the render kernel bulk-copies
-//   * gather_kernel    : static biases, conditioning columns, transposed direction columns
+// nfb_pack.cu — load-time, per-optimizer-step and per-frame preparation kernels (not on the per-ray hot path):
+//   * repack_kernel    : ONE launch per weight update: fc_feat pre-multiplied into fc_alpha and layers_dir.0[:, :256] (FP64
+//                        accumulate, computed where needed), FP32 weights -> FP16 hi/lo as the swizzled shared-memory images the
+//                        render kernels bulk-copy (forward streams) and the transposed stream of the backward chain, static
+//                        biases, conditioning columns, transposed direction columns
 //   * frame_fold_kernel: per-frame expression/latent fold into the layer-0 / layer-3 biases
 // Reference semantics: nerf/models.py:236-261 (forward), :218-233 (parameter shapes).
 #include <cuda_fp16.h>
@@ -13,45 +13,40 @@
 
 namespace nfb {
 
-// W6[144][256]: rows 0..127 = Wd0[:, :256] @ Wf, row 128 = wa @ Wf, rows 129..143 = 0.
-// b6[144]:      rows 0..127 = bd0 + Wd0[:, :256] @ bf, row 128 = ba + wa . bf.
-__global__ void fold_feat_kernel(const float* __restrict__ Wf, const float* __restrict__ bf, const float* __restrict__ wa,
-                                 const float* __restrict__ ba, const float* __restrict__ Wd0, const float* __restrict__ bd0,
-                                 float* __restrict__ W6, float* __restrict__ b6) {
-  const int n = blockIdx.x;   // 0..143
-  const int k = threadIdx.x;  // 0..255
-  if (n > 128) {
-    W6[n * 256 + k] = 0.f;
-    if (k == 0) b6[n] = 0.f;
-    return;
-  }
-  const float* left = (n < 128) ? (Wd0 + (size_t)n * 280) : wa;
+// Folded step-6 matrix, computed where it is needed (FP64 accumulate, like a separate fold pass would):
+//   W6[n][k], n < 128: (Wd0[:, :256] @ Wf)[n][k];  n == 128: (wa @ Wf)[k];  n > 128: 0
+//   b6[n],    n < 128: bd0[n] + Wd0[n, :256] . bf;  n == 128: ba + wa . bf
+struct NetParams { const float* p[26]; };  // state_dict order (nfb.h: nfb_load_weights)
+__device__ __forceinline__ float w6_elem(const NetParams& a, int n, int k) {
+  if (n > 128) return 0.f;
+  const float* left = (n < 128) ? (a.p[16] + (size_t)n * 280) : a.p[14];
+  const float* Wf = a.p[12];
   double acc = 0.0;
   for (int j = 0; j < 256; ++j) acc += (double)left[j] * (double)Wf[j * 256 + k];
-  W6[n * 256 + k] = (float)acc;
-  if (k == 0) {
-    double b = (n < 128) ? (double)bd0[n] : (double)ba[0];
-    for (int j = 0; j < 256; ++j) b += (double)left[j] * (double)bf[j];
-    b6[n] = (float)b;
-  }
+  return (float)acc;
 }
+__device__ __forceinline__ float b6_elem(const NetParams& a, int n) {
+  if (n > 128) return 0.f;
+  const float* left = (n < 128) ? (a.p[16] + (size_t)n * 280) : a.p[14];
+  const float* bf = a.p[13];
+  double b = (n < 128) ? (double)a.p[17][n] : (double)a.p[15][0];
+  for (int j = 0; j < 256; ++j) b += (double)left[j] * (double)bf[j];
+  return (float)b;
+}
+// step -> (source parameter index, leading dimension, valid output rows); step 6 is the folded matrix
+__device__ __forceinline__ int step_src(int s) { return s <= 5 ? 2 * s : (s == 7 ? 18 : (s == 8 ? 20 : 24)); }
+__device__ __forceinline__ int step_ld(int s) { return s == 0 ? 171 : (s == 3 ? 427 : (s <= 6 ? 256 : 128)); }
+__device__ __forceinline__ int step_rows(int s) { return s <= 5 ? 256 : (s == 6 ? 129 : (s == 9 ? 3 : 128)); }
 
-// One thread per 16-byte chunk (8 consecutive K) of one weight row of unit `u` (blockIdx.y) of step `s` (blockIdx.z).
-struct PackArgs {
-  const float* src[kNumSteps];  // step -> source matrix (row-major [out, in])
-  int ld[kNumSteps];            // leading dimension
-  int n_valid[kNumSteps];       // valid output rows
-};
-__global__ void pack_step_kernel(PackArgs a, uint8_t* __restrict__ dst_x1, uint8_t* __restrict__ dst_x3) {
-  const int s = blockIdx.z;
+// Forward streams: one thread per 16-byte chunk (8 consecutive K) of one weight row of unit `u` of step `s`.
+__device__ __forceinline__ void pack_fwd_chunk(const NetParams& a, int s, int u, int idx, uint8_t* __restrict__ dst_x1,
+                                               uint8_t* __restrict__ dst_x3) {
   const StepInfo si = step_info(s);
-  const int u = blockIdx.y;
   if (u >= num_units(s)) return;
-  const float* __restrict__ src = a.src[s];
-  const int ld = a.ld[s], n_valid = a.n_valid[s];
   const UnitInfo ui = unit_info(s, u);
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ui.rows * 8) return;
+  const float* __restrict__ src = a.p[step_src(s)];
+  const int ld = step_ld(s), n_valid = step_rows(s);
   const int c16 = idx & 7;
   const int n_local = idx >> 3;
   const int n = (ui.h ? si.nh0 : 0) + n_local;  // row of the step's logical weight matrix
@@ -62,7 +57,8 @@ __global__ void pack_step_kernel(PackArgs a, uint8_t* __restrict__ dst_x1, uint8
     const int k = ui.ka * 64 + c16 * 8 + e;  // logical K index of this step
     float w = 0.f;
     if (n < n_valid) {
-      if (si.pe_first) {
+      if (s == 6) w = w6_elem(a, n, k);
+      else if (si.pe_first) {
         if (k < kDimXyz) w = src[(size_t)n * ld + k];
         else if (k >= 64) w = src[(size_t)n * ld + (kDimXyz + kDimCond) + (k - 64)];
       } else {
@@ -80,18 +76,13 @@ __global__ void pack_step_kernel(PackArgs a, uint8_t* __restrict__ dst_x1, uint8
   *reinterpret_cast<uint4*>(dst_x3 + unit_x3 + (size_t)ui.rows * 128 + inner) = *reinterpret_cast<const uint4*>(lo);
 }
 
-// Static bias block, the 108 conditioning columns of layers_xyz.0/.3 and the transposed direction
-// columns of layers_dir.0.  `p` = the 26 parameter pointers, `b6` = folded step-6 bias.
-struct GatherArgs {
-  const float* p[26];
-};
-__global__ void gather_kernel(GatherArgs g, const float* __restrict__ b6, float* __restrict__ bias_static,
-                              float* __restrict__ w0c, float* __restrict__ w3c, float* __restrict__ wd0b_t) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// Static bias block, the 108 conditioning columns of layers_xyz.0/.3 and the transposed direction columns of layers_dir.0.
+__device__ __forceinline__ void gather_elem(const NetParams& g, int t, float* __restrict__ bias_static, float* __restrict__ w0c,
+                                            float* __restrict__ w3c, float* __restrict__ wd0b_t) {
   if (t < kBiasFloats) {
     float v = 0.f;
     if (t < 1536) v = g.p[2 * (t / 256) + 1][t % 256];       // layers_xyz.{0..5}.bias
-    else if (t < 1680) v = b6[t - 1536];                      // folded layers_dir.0 / fc_alpha
+    else if (t < 1680) v = b6_elem(g, t - 1536);              // folded layers_dir.0 / fc_alpha
     else if (t < 1808) v = g.p[19][t - 1680];                 // layers_dir.1.bias
     else if (t < 1936) v = g.p[21][t - 1808];                 // layers_dir.2.bias
     else if (t < 1939) v = g.p[25][t - 1936];                 // fc_rgb.bias
@@ -108,15 +99,95 @@ __global__ void gather_kernel(GatherArgs g, const float* __restrict__ b6, float*
   }
 }
 
-// bias_frame = bias_static, then rows of step 0 and step 3 += W[:, 63:171] . [expr/3 ; latent].
-__global__ void frame_fold_kernel(const float* __restrict__ expr, const float* __restrict__ latent,
-                                  const float* __restrict__ bias_static, const float* __restrict__ w0c,
-                                  const float* __restrict__ w3c, float* __restrict__ bias_frame) {
+// Backward (transposed) stream: one thread per 16-byte chunk (8 consecutive k) of row n of unit (s, u); element (n, k) = W^T.
+__device__ __forceinline__ void pack_bwd_chunk(const NetParams& a, int s, int u, int idx, uint8_t* __restrict__ dst) {
+  const StepInfo si = bwd_step_info(s);
+  if (u >= si.k_atoms) return;
+  const int rows = si.nh0 + si.nh1;
+  if (idx >= rows * 8) return;
+  const int c16 = idx & 7, n = idx >> 3;
+  const bool op_atom = si.pe_first && u == 0;
+  const int hid = u - si.pe_first;  // TMEM atom index
+  __align__(16) __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int kl = c16 * 8 + e;        // k inside the atom
+    const int kk = hid * 64 + kl;      // output-feature index of the forward layer (TMEM atoms)
+    float w = 0.f;
+    switch (s) {
+      case 0: if (kl < 3) w = a.p[24][kl * 128 + n]; break;                       // fc_rgb.weight[kl][n]
+      case 1: w = a.p[20][kk * 128 + n]; break;                                    // layers_dir.2.weight[kk][n]
+      case 2: w = a.p[18][kk * 128 + n]; break;                                    // layers_dir.1
+      case 3: if (op_atom) { if (kl == 3) w = w6_elem(a, 128, n); }                // m2 = fc_alpha . fc_feat
+              else w = w6_elem(a, kk, n); break;                                   // M1 = layers_dir.0[:, :256] . fc_feat
+      case 4: w = a.p[10][kk * 256 + n]; break;                                    // layers_xyz.5
+      case 5: w = a.p[8][kk * 256 + n]; break;                                     // layers_xyz.4
+      case 6: w = a.p[6][(size_t)kk * 427 + (kDimXyz + kDimCond) + n]; break;      // layers_xyz.3[:, 171:]
+      case 7: w = a.p[4][kk * 256 + n]; break;                                     // layers_xyz.2
+      default: w = a.p[2][kk * 256 + n]; break;                                    // layers_xyz.1
+    }
+    h[e] = __float2half_rn(w);
+  }
+  const int off = bwd_step_offset(s) + u * rows * 128;
+  *reinterpret_cast<uint4*>(dst + off + n * 128 + ((c16 ^ (n & 7)) << 4)) = *reinterpret_cast<const uint4*>(h);
+}
+
+// ONE launch re-packs up to two networks: FP32 parameters -> forward streams (x1, hi/lo x3), transposed backward stream,
+// bias block, conditioning columns, direction columns.  Block ranges per network: [0, kFwdBlocks) forward chunks (8 blocks
+// per (step, unit)), then backward chunks, then the gather.  Used by nfb_load_weights and by the fused optimizer step.
+constexpr int kMaxFwdUnits = 5, kMaxBwdUnits = 4;
+constexpr int kFwdBlocks = 8 * kMaxFwdUnits * kNumSteps;   // 400
+constexpr int kBwdBlocks = 8 * kMaxBwdUnits * kBwdSteps;   // 288
+constexpr int kGatherBlocks = (256 * kDimCond + 255) / 256;  // 108
+constexpr int kRepackBlocks = kFwdBlocks + kBwdBlocks + kGatherBlocks;
+struct RepackArgs {
+  NetParams net[2];
+  uint8_t *x1[2], *x3[2], *bwd[2];
+  float *bias_static[2], *w0c[2], *w3c[2], *wd0b_t[2];
+};
+__global__ void __launch_bounds__(256) repack_kernel(const RepackArgs a) {
+  const int net = blockIdx.y;
+  int b = blockIdx.x;
+  const NetParams& np = a.net[net];
+  if (b < kFwdBlocks) {
+    const int s = b / (8 * kMaxFwdUnits), r = b % (8 * kMaxFwdUnits);
+    pack_fwd_chunk(np, s, r / 8, (r % 8) * 256 + threadIdx.x, a.x1[net], a.x3[net]);
+    return;
+  }
+  b -= kFwdBlocks;
+  if (b < kBwdBlocks) {
+    const int s = b / (8 * kMaxBwdUnits), r = b % (8 * kMaxBwdUnits);
+    pack_bwd_chunk(np, s, r / 8, (r % 8) * 256 + threadIdx.x, a.bwd[net]);
+    return;
+  }
+  b -= kBwdBlocks;
+  gather_elem(np, b * 256 + threadIdx.x, a.bias_static[net], a.w0c[net], a.w3c[net], a.wd0b_t[net]);
+}
+
+// Per-frame conditioning in ONE launch.  Blocks 0..n_nets-1: bias_frame = bias_static, then rows of step 0 and step 3
+// += W[:, 63:171] . [expr/3 ; latent] of that network.  Last block: cond[108] = [expr/3 ; latent] (the backward's chain rule
+// through this fold needs it).
+struct FrameFoldArgs {
+  const float *bias_static[2], *w0c[2], *w3c[2];
+  float* bias_frame[2];
+  float* cond;
+  int n_nets;
+};
+__global__ void frame_fold_kernel(const float* __restrict__ expr, const float* __restrict__ latent, const FrameFoldArgs a) {
   __shared__ float c[kDimCond];
   const int t = threadIdx.x;
   if (t < kDimExpr) c[t] = __fdiv_rn(expr[t], 3.0f);  // (expr * 1 / 3), models.py:241
   else if (t < kDimCond) c[t] = latent[t - kDimExpr];
   __syncthreads();
+  const int net = blockIdx.x;
+  if (net >= a.n_nets) {
+    if (t < kDimCond) a.cond[t] = c[t];
+    return;
+  }
+  const float* __restrict__ bias_static = a.bias_static[net];
+  const float* __restrict__ w0c = a.w0c[net];
+  const float* __restrict__ w3c = a.w3c[net];
+  float* __restrict__ bias_frame = a.bias_frame[net];
   for (int i = t; i < kBiasFloats; i += blockDim.x) {
     float v = bias_static[i];
     const float* w = nullptr;
@@ -132,31 +203,28 @@ __global__ void frame_fold_kernel(const float* __restrict__ expr, const float* _
   }
 }
 
-cudaError_t launch_load_weights(NetBuffers& nb, const float* const params[26], cudaStream_t st, long long* launches) {
-  fold_feat_kernel<<<144, 256, 0, st>>>(params[12], params[13], params[14], params[15], params[16], params[17], nb.w6,
-                                        nb.b6);
-  ++*launches;
-  GatherArgs g;
-  for (int i = 0; i < 26; ++i) g.p[i] = params[i];
-  gather_kernel<<<(256 * kDimCond + 255) / 256, 256, 0, st>>>(g, nb.b6, nb.bias_static, nb.w0c, nb.w3c, nb.wd0b_t);
-  ++*launches;
-  // step -> (source matrix, leading dimension, valid rows); one launch packs every unit of every step
-  PackArgs a;
-  const float* src[kNumSteps] = {params[0], params[2], params[4], params[6], params[8], params[10], nb.w6, params[18], params[20], params[24]};
-  const int ld[kNumSteps] = {171, 256, 256, 427, 256, 256, 256, 128, 128, 128};
-  const int nv[kNumSteps] = {256, 256, 256, 256, 256, 256, 129, 128, 128, 3};
-  int max_units = 0;
-  for (int s = 0; s < kNumSteps; ++s) {
-    a.src[s] = src[s]; a.ld[s] = ld[s]; a.n_valid[s] = nv[s];
-    if (num_units(s) > max_units) max_units = num_units(s);
+cudaError_t launch_repack(NetBuffers* const nb[2], const float* const* const params[2], int n_nets, cudaStream_t st,
+                          long long* launches) {
+  RepackArgs a;
+  for (int n = 0; n < n_nets; ++n) {
+    for (int i = 0; i < 26; ++i) a.net[n].p[i] = params[n][i];
+    a.x1[n] = nb[n]->stream_x1; a.x3[n] = nb[n]->stream_x3; a.bwd[n] = nb[n]->stream_bwd;
+    a.bias_static[n] = nb[n]->bias_static; a.w0c[n] = nb[n]->w0c; a.w3c[n] = nb[n]->w3c; a.wd0b_t[n] = nb[n]->wd0b_t;
   }
-  pack_step_kernel<<<dim3(8, max_units, kNumSteps), 256, 0, st>>>(a, nb.stream_x1, nb.stream_x3);
+  repack_kernel<<<dim3(kRepackBlocks, n_nets), 256, 0, st>>>(a);
   ++*launches;
   return cudaGetLastError();
 }
 
-cudaError_t launch_frame_fold(NetBuffers& nb, const float* expr, const float* latent, cudaStream_t st, long long* launches) {
-  frame_fold_kernel<<<1, 256, 0, st>>>(expr, latent, nb.bias_static, nb.w0c, nb.w3c, nb.bias_frame);
+cudaError_t launch_frame_fold(NetBuffers* const nb[2], int n_nets, const float* expr, const float* latent, float* cond,
+                              cudaStream_t st, long long* launches) {
+  FrameFoldArgs a;
+  for (int n = 0; n < n_nets; ++n) {
+    a.bias_static[n] = nb[n]->bias_static; a.w0c[n] = nb[n]->w0c; a.w3c[n] = nb[n]->w3c; a.bias_frame[n] = nb[n]->bias_frame;
+  }
+  a.cond = cond;
+  a.n_nets = n_nets;
+  frame_fold_kernel<<<n_nets + 1, 256, 0, st>>>(expr, latent, a);
   ++*launches;
   return cudaGetLastError();
 }

@@ -134,50 +134,7 @@ __host__ __device__ constexpr BwdUnit bwd_unit_info(int s, int u) {
 }
 __host__ __device__ constexpr int bwd_unit_offset(int s, int u) { return bwd_step_offset(s) + u * (bwd_step_info(s).nh0 + bwd_step_info(s).nh1) * 128; }
 
-struct PackBwdArgs { const float* p[26]; const float* w6; };
-// One thread per 16-byte chunk (8 consecutive k) of one row n of unit (s = blockIdx.z, u = blockIdx.y).
-__global__ void pack_bwd_kernel(PackBwdArgs a, uint8_t* __restrict__ dst) {
-  const int s = blockIdx.z;
-  const StepInfo si = bwd_step_info(s);
-  const int u = blockIdx.y;
-  if (u >= si.k_atoms) return;
-  const int rows = si.nh0 + si.nh1;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * 8) return;
-  const int c16 = idx & 7, n = idx >> 3;
-  const bool op_atom = si.pe_first && u == 0;
-  const int hid = u - si.pe_first;  // TMEM atom index
-  __align__(16) __half h[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int kl = c16 * 8 + e;        // k inside the atom
-    const int kk = hid * 64 + kl;      // output-feature index of the forward layer (TMEM atoms)
-    float w = 0.f;
-    switch (s) {
-      case 0: if (kl < 3) w = a.p[24][kl * 128 + n]; break;                       // fc_rgb.weight[kl][n]
-      case 1: w = a.p[20][kk * 128 + n]; break;                                    // layers_dir.2.weight[kk][n]
-      case 2: w = a.p[18][kk * 128 + n]; break;                                    // layers_dir.1
-      case 3: if (op_atom) { if (kl == 3) w = a.w6[128 * 256 + n]; }               // m2 = fc_alpha . fc_feat
-              else w = a.w6[kk * 256 + n]; break;                                  // M1 = layers_dir.0[:, :256] . fc_feat
-      case 4: w = a.p[10][kk * 256 + n]; break;                                    // layers_xyz.5
-      case 5: w = a.p[8][kk * 256 + n]; break;                                     // layers_xyz.4
-      case 6: w = a.p[6][(size_t)kk * 427 + (kDimXyz + kDimCond) + n]; break;      // layers_xyz.3[:, 171:]
-      case 7: w = a.p[4][kk * 256 + n]; break;                                     // layers_xyz.2
-      default: w = a.p[2][kk * 256 + n]; break;                                    // layers_xyz.1
-    }
-    h[e] = __float2half_rn(w);
-  }
-  *reinterpret_cast<uint4*>(dst + bwd_unit_offset(s, u) + n * 128 + ((c16 ^ (n & 7)) << 4)) = *reinterpret_cast<const uint4*>(h);
-}
-
-cudaError_t launch_pack_bwd(NetBuffers& nb, const float* const params[26], cudaStream_t st, long long* launches) {
-  PackBwdArgs a;
-  for (int i = 0; i < 26; ++i) a.p[i] = params[i];
-  a.w6 = nb.w6;
-  pack_bwd_kernel<<<dim3(8, 4, kBwdSteps), 256, 0, st>>>(a, nb.stream_bwd);
-  ++*launches;
-  return cudaGetLastError();
-}
+// (the transposed stream is written by repack_kernel, nfb_pack.cu)
 
 // ================================================================================================
 // 2. dX chain kernel
@@ -803,12 +760,6 @@ __global__ void latent_grad_kernel(const LatArgs a) {  // one block of 256 threa
   }
 }
 
-__global__ void cond_kernel(const float* __restrict__ expr, const float* __restrict__ latent, float* __restrict__ cond) {
-  const int t = threadIdx.x;
-  if (t < kDimExpr) cond[t] = __fdiv_rn(expr[t], 3.0f);
-  else if (t < kDimCond) cond[t] = latent[t - kDimExpr];
-}
-
 // ================================================================================================
 // host-side launchers
 // ================================================================================================
@@ -836,12 +787,6 @@ cudaError_t train_kernels_setup() {
   cudaError_t e = cudaFuncSetAttribute(chain::chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::kSmemBytes);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(dw::dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dw::kSmemBytes);
-}
-
-cudaError_t launch_cond(const float* expr, const float* latent, float* cond, cudaStream_t st, long long* launches) {
-  cond_kernel<<<1, 128, 0, st>>>(expr, latent, cond);
-  ++*launches;
-  return cudaGetLastError();
 }
 
 cudaError_t launch_composite_bwd(const CompBwdParams& q, float* scal, cudaStream_t st, long long* launches) {

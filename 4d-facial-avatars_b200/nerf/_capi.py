@@ -12,7 +12,8 @@ NFB_PREC_FAST, NFB_PREC_EXACT = 0, 1
 
 EXPORTS = ["nfb_version", "nfb_strerror", "nfb_last_cuda_error", "nfb_create", "nfb_destroy", "nfb_load_weights",
            "nfb_set_frame", "nfb_render_forward", "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace",
-           "nfb_render_forward_train", "nfb_render_backward", "nfb_train_debug", "nfb_debug_schedule"]
+           "nfb_render_forward_train", "nfb_render_backward", "nfb_train_debug", "nfb_debug_schedule", "nfb_loss_mse_grad",
+           "nfb_adam_step", "nfb_repack"]
 
 
 class NfbModelDims(C.Structure):
@@ -58,6 +59,11 @@ class NfbTrainDebug(C.Structure):
                 ("tiles_coarse", C.c_int32), ("tiles_fine", C.c_int32), ("rays_per_unit", C.c_int32)]
 
 
+class NfbAdam(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int32),
+                ("grad_scale", C.c_float), ("reg_offset", C.c_longlong), ("reg_weight", C.c_float)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} not found: build it with `python 4d-facial-avatars_b200/build.py` "
@@ -81,11 +87,15 @@ def _load():
     lib.nfb_render_backward.argtypes = [C.c_void_p, C.POINTER(NfbOutGrads), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
     lib.nfb_train_debug.argtypes = [C.c_void_p, C.POINTER(NfbTrainDebug)]
+    lib.nfb_loss_mse_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+    lib.nfb_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(NfbAdam), C.c_void_p]
+    lib.nfb_repack.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
     lib.nfb_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     lib.nfb_host_linspace.argtypes = [C.POINTER(C.c_float), C.c_int]
     for fn in ("nfb_create", "nfb_destroy", "nfb_load_weights", "nfb_set_frame", "nfb_render_forward",
                "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace", "nfb_render_forward_train",
-               "nfb_render_backward", "nfb_train_debug"):
+               "nfb_render_backward", "nfb_train_debug", "nfb_loss_mse_grad", "nfb_adam_step", "nfb_repack"):
         getattr(lib, fn).restype = C.c_int
     return lib
 

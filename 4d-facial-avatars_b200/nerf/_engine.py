@@ -62,8 +62,20 @@ class Renderer:
 
     @staticmethod
     def _fingerprint(model):
+        """(identity, storage, in-place version) of every parameter.  Writes that bypass autograd's version counter
+        (`p.data.copy_()`, external kernels) are invisible here: call invalidate() after them."""
         sd = dict(model.named_parameters())
-        return tuple((sd[k].data_ptr(), sd[k]._version) for k in PARAM_ORDER)
+        return (id(model),) + tuple((sd[k].data_ptr(), sd[k]._version) for k in PARAM_ORDER)
+
+    def invalidate(self):
+        """Force a re-pack of both networks at the next render (after parameter writes torch cannot see)."""
+        self._versions = [None, None]
+
+    def mark_synced(self, model_coarse, model_fine):
+        """The packed streams already hold these models' current values (the fused optimizer step re-packed them)."""
+        self._versions[0] = self._fingerprint(model_coarse)
+        if model_fine is not None:
+            self._versions[1] = self._fingerprint(model_fine)
 
     def sync_weights(self, model_coarse, model_fine):
         for which, model in ((capi.NFB_NET_COARSE, model_coarse), (capi.NFB_NET_FINE, model_fine)):
@@ -94,6 +106,15 @@ class Renderer:
             raise ValueError("expressions must have 76 and latent_code 32 elements")
         capi.check(capi.lib.nfb_set_frame(self._h, _ptr(e), _ptr(l), _stream()), "set_frame")
         self._frame = (e, l)
+
+    def kernel_info(self, precision="fast"):
+        """Which render kernel an evaluation call in this precision runs, and the ncu capture that describes it (bench.py)."""
+        k = os.environ.get("NFB_KERNEL", "")
+        if precision != "fast" or k == "v4":
+            return dict(name="nfb::render_kernel", block_size=320, ncu_json="r2_render_kernel_exact_ncu.json")
+        if k == "v6":
+            return dict(name="nfb::v6::render2_kernel", block_size=384, ncu_json="r2_render2_kernel_ncu.json")
+        return dict(name="nfb::v7::render3_kernel", block_size=512, ncu_json="r2_render3_kernel_ncu.json")
 
     def launch_count(self) -> int:
         n = C.c_longlong()
@@ -166,6 +187,40 @@ class Renderer:
                        "render_forward")
         out["_keep"] = keep  # inputs must outlive the asynchronous launch
         return out
+
+    def loss_mse_grad(self, rgb_c, rgb_f, target, n_total, grad_c, grad_f, loss):
+        """nfb_loss_mse_grad: d mse / d rgb into grad_c / grad_f ([n,3] CUDA buffers), loss[0:2] += this shard's share."""
+        n = rgb_c.shape[0]
+        capi.check(capi.lib.nfb_loss_mse_grad(self._h, _ptr(rgb_c), _ptr(rgb_f), _ptr(target), n, int(n_total), _ptr(grad_c),
+                                              _ptr(grad_f), _ptr(loss), _stream()), "loss_mse_grad")
+
+    def adam_step(self, params, grads, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0,
+                  reg_offset=-1, reg_weight=0.0):
+        """nfb_adam_step over flat FP32 CUDA buffers (in place; grads are zeroed)."""
+        hp = capi.NfbAdam(float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), float(grad_scale), int(reg_offset),
+                          float(reg_weight))
+        capi.check(capi.lib.nfb_adam_step(self._h, _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(),
+                                          C.byref(hp), _stream()), "adam_step")
+
+    def repack(self, params_c, params_f):
+        """nfb_repack: both networks' FP32 parameter tensors (lists in PARAM_ORDER) -> kernel-layout streams, one launch."""
+        pc = (C.c_void_p * 26)(*[t.data_ptr() for t in params_c])
+        pf = (C.c_void_p * 26)(*[t.data_ptr() for t in params_f]) if params_f is not None else None
+        capi.check(capi.lib.nfb_repack(self._h, pc, pf, _stream()), "repack")
+
+    def backward_into(self, out_grads, params_c, params_f, grads_c, grads_f, grad_latent):
+        """nfb_render_backward writing straight into caller-owned gradient tensors (views of a flat bucket): params_* / grads_*
+        are lists of 26 contiguous FP32 CUDA tensors in PARAM_ORDER (grads of layers_dir.3.* may be None)."""
+        og = capi.NfbOutGrads()
+        keep = []
+        for field, g in zip(("rgb_coarse", "disp_coarse", "acc_coarse", "rgb_fine", "disp_fine", "acc_fine", "w_last"), out_grads):
+            if g is not None:
+                keep.append(g)
+                setattr(og, field, g.data_ptr())
+        arr = lambda ts: (C.c_void_p * 26)(*[(t.data_ptr() if t is not None else None) for t in ts]) if ts is not None else None  # noqa: E731
+        capi.check(capi.lib.nfb_render_backward(self._h, C.byref(og), arr(params_c), arr(params_f), arr(grads_c), arr(grads_f),
+                                                _ptr(grad_latent), _stream()), "render_backward")
+        self._bwd_keep = keep
 
     def backward(self, out_grads, params_c, params_f, want_latent=True):
         """nfb_render_backward for the last training forward.  out_grads: 7 CUDA tensors or None (rgb_c, disp_c, acc_c,

@@ -5,6 +5,8 @@ shards the ray batch and all-reduces one flat FP32 gradient bucket.  One process
 import torch
 import torch.distributed as dist
 
+from . import train_utils
+
 
 def shard_rows(height: int, world: int, rank: int):
     """Contiguous row block [begin, begin+rows) of rank `rank`; the first height % world ranks get one extra row."""
@@ -99,7 +101,9 @@ def data_parallel(run_fn, group=None):
       (allreduce_gradients(average=True), e.g. from an optimizer pre-step hook) yields exactly the single-process gradient —
       including loss terms that do not depend on the rays (the latent-code regulariser), which every rank computes alike.
 
-    Noise: each rank draws its own shard's noise, so stochastic runs match the single-process run in distribution only."""
+    Noise: every rank draws the noise of the WHOLE call in the reference's order and keeps its shard's slice
+    (train_utils._shard_ctx), so a seeded multi-rank run renders exactly what the seeded single-process run renders and the
+    ranks' RNG streams stay in lock-step for the caller's own draws (ray selection)."""
     def wrapped(height, width, focal_length, model_coarse, model_fine, ray_origins, ray_directions, options, mode="train",
                 encode_position_fn=None, encode_direction_fn=None, expressions=None, background_prior=None, latent_code=None,
                 ray_directions_ablation=None):
@@ -113,17 +117,25 @@ def data_parallel(run_fn, group=None):
             begin, rows = shard_rows(H, world, rank)
             sl = slice(begin, begin + rows)
             bg = background_prior.reshape(H, W, 3)[sl].reshape(-1, 3) if background_prior is not None else None
-            abl = ray_directions_ablation.reshape(H, W, 3)[sl] if torch.is_tensor(ray_directions_ablation) else ray_directions_ablation
-            outs = run_fn(rows, width, focal_length, model_coarse, model_fine, ray_origins[sl], ray_directions[sl], options, mode,
-                          encode_position_fn, encode_direction_fn, expressions, bg, latent_code, abl)
+            abl = ray_directions_ablation  # the whole bundle: train_utils slices it by the single-process chunk rule (_shard_ctx)
+            train_utils._shard_ctx = (begin * W, rows * W, H * W)
+            try:
+                outs = run_fn(rows, width, focal_length, model_coarse, model_fine, ray_origins[sl], ray_directions[sl], options, mode,
+                              encode_position_fn, encode_direction_fn, expressions, bg, latent_code, abl)
+            finally:
+                train_utils._shard_ctx = None
             return tuple(gather_rows(o.contiguous(), H, group) if o is not None else None for o in outs)
         n = ray_directions.shape[0]
         begin, per = shard_batch(n, world, rank)
         sl = slice(begin, begin + per)
         bg = background_prior[sl] if background_prior is not None else None
-        abl = ray_directions_ablation[sl] if torch.is_tensor(ray_directions_ablation) else ray_directions_ablation
-        outs = run_fn(height, width, focal_length, model_coarse, model_fine, ray_origins[sl], ray_directions[sl], options, mode,
-                      encode_position_fn, encode_direction_fn, expressions, bg, latent_code, abl)
+        abl = ray_directions_ablation
+        train_utils._shard_ctx = (begin, per, n)
+        try:
+            outs = run_fn(height, width, focal_length, model_coarse, model_fine, ray_origins[sl], ray_directions[sl], options, mode,
+                          encode_position_fn, encode_direction_fn, expressions, bg, latent_code, abl)
+        finally:
+            train_utils._shard_ctx = None
         full = []
         for o in outs:
             if o is None:

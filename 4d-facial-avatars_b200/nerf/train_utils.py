@@ -37,6 +37,13 @@ def _draw_noise(n, opts, device, has_fine):
     return out
 
 
+# Set by nerf/parallel.py: data_parallel while it calls run_one_iter_of_nerf on one shard (begin, count) of a call that has
+# n_full rays in the single-process program.  The noise is then drawn for ALL n_full rays in the reference's chunk order and
+# sliced, so (a) every rank consumes the RNG stream exactly like the single-process run (the streams stay in lock-step for the
+# script's own np.random / torch draws) and (b) the shards see independent noise — the same noise the unsharded run would.
+_shard_ctx = None
+
+
 def _cat_noise(chunks):
     return {k: (torch.cat([c[k] for c in chunks], dim=0) if chunks[0][k] is not None else None) for k in chunks[0]}
 
@@ -107,17 +114,28 @@ def run_one_iter_of_nerf(height, width, focal_length, model_coarse, model_fine, 
     bounds = list(range(0, n, chunk))
     dir_z = None
     if torch.is_tensor(ray_directions_ablation):
+        # every chunk sees chunk 0 of the ablation bundle (train_utils.py:81-82).  Under data_parallel the bundle is the WHOLE
+        # call's and the chunks are the single-process program's; this shard keeps its slice.
+        n_all = _shard_ctx[2] if _shard_ctx is not None else n
         fake0 = ray_directions_ablation.reshape(-1, 3)[:chunk]
         parts = []
-        for st in bounds:
-            m = min(chunk, n - st)
+        for st in range(0, n_all, chunk):
+            m = min(chunk, n_all - st)
             if fake0.shape[0] != m:
                 raise RuntimeError(f"shape mismatch: ray chunk has {m} rays, ablation chunk 0 has {fake0.shape[0]}")
             parts.append(fake0[:, 2])
         dir_z = torch.cat(parts, dim=0)
+        if _shard_ctx is not None:
+            dir_z = dir_z[_shard_ctx[0]:_shard_ctx[0] + _shard_ctx[1]].contiguous()
     noise = None
     if opts["perturb"] or opts["noise_std"] > 0.0:
-        noise = _cat_noise([_draw_noise(min(chunk, n - st), opts, rays.device, has_fine) for st in bounds])
+        if _shard_ctx is not None:
+            begin, count, n_full = _shard_ctx
+            assert count == n
+            full = _cat_noise([_draw_noise(min(chunk, n_full - st), opts, rays.device, has_fine) for st in range(0, n_full, chunk)])
+            noise = {k: (v[begin:begin + count].contiguous() if v is not None else None) for k, v in full.items()}
+        else:
+            noise = _cat_noise([_draw_noise(min(chunk, n - st), opts, rays.device, has_fine) for st in bounds])
     bg = background_prior.reshape(-1, 3) if background_prior is not None else None
     outs = list(_render(rays, options.dataset.near, options.dataset.far, model_coarse, model_fine if has_fine else None, opts, expressions, bg, latent_code, dir_z, noise))
     if mode == "validation":

@@ -392,7 +392,7 @@ def bench_train(c, steps, warmup, impl, rays=2048, nc=64, nf=64):
         sync_all(c)
         tot = sum(e[0].elapsed_time(e[3]) for e in evs) / k
         coll = sum(e[1].elapsed_time(e[2]) for e in evs) / k
-        return tot, coll, float(last)
+        return tot, coll, float(last.sum())
 
     k = 0
     for j in range(max(3, warmup)):  # single-GPU warm-up (packs, allocations)

@@ -13,7 +13,7 @@
  * (0 = NFB_OK) and never throws; nfb_strerror() maps it to text.  All device pointers are FP32,
  * row-major, 16-byte aligned, on the device the handle was created for.  Calls are asynchronous on
  * the given cudaStream_t (passed as void*) unless stated otherwise; no entry synchronises the device
- * except nfb_render_frame_host and nfb_selftest.
+ * except nfb_render_frame_host.
  */
 #ifndef NFB_H_
 #define NFB_H_
@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NFB_VERSION 110
+#define NFB_VERSION 120
 
 typedef struct NfbHandle NfbHandle;
 
@@ -185,6 +185,36 @@ typedef struct {
 int nfb_render_backward(NfbHandle* h, const NfbOutGrads* out_grads, const float* const params_coarse[26],
                         const float* const params_fine[26], float* const grads_coarse[26], float* const grads_fine[26],
                         float* grad_latent, void* stream);
+
+/* ---- Training-step tail: loss, optimizer, re-pack (replaces train_transformed_rays.py:355-400 for callers that adopt it;
+ * the drop-in Python surface keeps working with torch.nn.functional.mse_loss + torch.optim.Adam) ----
+ *
+ * nfb_loss_mse_grad: d/d rgb of mse(rgb_coarse, target) + mse(rgb_fine, target) (train_transformed_rays.py:355-362, 382), the
+ * means taken over n_total * 3 elements — n_total is the GLOBAL batch size when the n_rays of this call are one shard of it, so
+ * that a SUM all-reduce of the parameter gradients gives the single-process gradient.  Writes grad_rgb_* [n_rays,3] (feed them
+ * to nfb_render_backward) and ADDS this shard's share of the two loss values to loss[0], loss[1] (zero them first).  1 launch. */
+int nfb_loss_mse_grad(NfbHandle* h, const float* rgb_coarse, const float* rgb_fine /* nullable */, const float* target,
+                      int n_rays, long long n_total, float* grad_rgb_coarse, float* grad_rgb_fine, float* loss, void* stream);
+
+/* torch.optim.Adam (betas, eps as given; no weight decay / amsgrad; YAML optimizer block) over ONE flat FP32 bucket of n
+ * floats — the caller lays out both networks' parameters and the latent-code table in it and hands views of it to
+ * nfb_render_backward as gradient targets, so neither a gradient copy nor a torch.cat precedes an all-reduce.  In place:
+ * params, exp_avg, exp_avg_sq are updated, grads are multiplied by grad_scale before use and ZEROED afterwards
+ * (optimizer.zero_grad()).  The latent-code regulariser 10 * 0.0005 * ||latent||_2 (train_transformed_rays.py:369-372, 386) is
+ * applied here: reg_weight * l / ||l|| is added to the gradient of the 32 floats at reg_offset (reg_offset < 0: none).
+ * `step` counts from 1; `lr` is this step's learning rate (the caller evaluates the schedule of :393-399).  1 launch. */
+typedef struct {
+  float lr, beta1, beta2, eps;
+  int32_t step;
+  float grad_scale;
+  long long reg_offset;
+  float reg_weight;
+} NfbAdam;
+int nfb_adam_step(NfbHandle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, const NfbAdam* hp,
+                  void* stream);
+
+/* nfb_load_weights for both networks in ONE launch (params_fine may be NULL): the re-pack after an optimizer step. */
+int nfb_repack(NfbHandle* h, const float* const params_coarse[26], const float* const params_fine[26], void* stream);
 
 /* Test hook: device pointers of the training state (valid until the next forward_train on the handle). */
 typedef struct {

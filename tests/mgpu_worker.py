@@ -1,0 +1,121 @@
+"""Worker of tests/test_multigpu.py — run under torch.distributed.run with one rank per GPU (NCCL).  Each check compares the
+multi-GPU path with the same work done by ONE GPU in the same process; rank 0 prints `MGPU_OK <name>` per check."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "4d-facial-avatars_b200")):
+    sys.path.insert(0, p)
+import nerface_oracle as O  # noqa: E402
+import nerf  # noqa: E402
+from nerf import _engine, fused_train, parallel  # noqa: E402
+
+NAMES = ["rgb_coarse", "disp_coarse", "acc_coarse", "rgb_fine", "disp_fine", "acc_fine", "w_last"]
+
+
+def make_model(params, dev):
+    m = nerf.models.ConditionalBlendshapePaperNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4,
+                                                        include_input_xyz=True, include_input_dir=False)
+    m.load_state_dict(params)
+    return m.to(dev)
+
+
+def main():
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    eng = _engine.renderer_for(dev)
+    ok = lambda name: rank == 0 and print("MGPU_OK", name, flush=True)  # noqa: E731
+
+    # ---- 1. eval: one frame sharded by pixel rows, packed 11-float tiles all-gathered == the single-GPU frame, bit for bit
+    H = W = 128
+    fr = O.synthetic_frame(4, H, W)
+    mc, mf = make_model(O.random_init_params(100, True), dev), make_model(O.random_init_params(101, True), dev)
+    eng.sync_weights(mc, mf)
+    eng.set_frame(fr["expr"].to(dev), fr["latent"].to(dev))
+    bg = fr["bg"].reshape(-1, 3).to(dev).contiguous()
+    full = eng.render_camera(fr["pose"], fr["intrinsics"], H, W, 0, H, 0.2, 0.8, 64, 128, background=bg)
+    begin, rows = parallel.shard_rows(H, world, rank)
+    loc = eng.render_camera(fr["pose"], fr["intrinsics"], H, W, begin, rows, 0.2, 0.8, 64, 128,
+                            background=bg[begin * W:(begin + rows) * W].contiguous())
+    for k in NAMES:
+        tile = loc[k].reshape(rows, W, -1)
+        whole = parallel.gather_rows(tile, H)
+        assert torch.equal(whole.reshape(full[k].shape), full[k]), k
+    ok("rows_bit_identical")
+
+    # ---- 2. the wrapper the unmodified eval script gets (validation mode): sharded == single process
+    blk = dict(num_coarse=64, num_fine=128, perturb=False, lindisp=False, radiance_field_noise_std=0.0, white_background=False, chunksize=65536)
+    cfg = nerf.CfgNode(dict(nerf=dict(use_viewdirs=True, validation=blk, train=dict(blk, num_fine=64, chunksize=2048)),
+                            dataset=dict(no_ndc=True, near=0.2, far=0.8)))
+    ro, rd = nerf.get_ray_bundle(H, W, fr["intrinsics"], fr["pose"].to(dev))
+    kw = dict(expressions=fr["expr"].to(dev), background_prior=bg, latent_code=fr["latent"].to(dev))
+    with torch.no_grad():
+        single = nerf.run_one_iter_of_nerf(H, W, fr["intrinsics"], mc, mf, ro, rd, cfg, mode="validation", **kw)
+        dp = parallel.data_parallel(nerf.run_one_iter_of_nerf)(H, W, fr["intrinsics"], mc, mf, ro, rd, cfg, mode="validation", **kw)
+    for a, b in zip(single, dp):
+        assert a.shape == b.shape and torch.equal(a, b)
+    ok("dp_validation_bit_identical")
+
+    # ---- 3. train through the wrapper + ONE averaging all-reduce of a flat bucket == single-process gradients
+    n = 256
+    g = torch.Generator().manual_seed(5)
+    sel = torch.randperm(H * W, generator=g)[:n].to(dev)
+    tgt = torch.rand(n, 3, generator=g).to(dev)
+    ro_f, rd_f = ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]
+
+    def grads_of(run, shard):
+        m1, m2 = make_model(O.random_init_params(100), dev), make_model(O.random_init_params(101), dev)
+        lat = torch.full((32,), 0.02, device=dev, requires_grad=True)
+        out = run(H, W, fr["intrinsics"], m1, m2, ro_f, rd_f, cfg, mode="train", expressions=fr["expr"].to(dev),
+                  background_prior=bg[sel], latent_code=lat)
+        loss = ((out[0] - tgt) ** 2).mean() + ((out[3] - tgt) ** 2).mean() + 0.005 * lat.norm()
+        loss.backward()
+        params = [p for p in list(m1.parameters()) + list(m2.parameters())] + [lat]
+        if shard:
+            parallel.allreduce_gradients(params, average=True)
+        return [p.grad.clone() for p in params if p.grad is not None], float(loss)
+
+    g1, l1 = grads_of(nerf.run_one_iter_of_nerf, False)
+    g2, l2 = grads_of(parallel.data_parallel(nerf.run_one_iter_of_nerf), True)
+    assert abs(l1 - l2) < 1e-6, (l1, l2)
+    for a, b in zip(g1, g2):
+        assert float((a - b).abs().max()) <= 2e-5 * max(float(a.abs().max()), 1e-6), float((a - b).abs().max())
+    ok("dp_train_gradients")
+
+    # ---- 4. fused trainer: the batch sharded over the ranks + one flat SUM all-reduce == the whole batch on one GPU
+    def trainer():
+        return fused_train.FusedTrainer(make_model(O.random_init_params(100), dev), make_model(O.random_init_params(101), dev),
+                                        n_latent=4, num_coarse=64, num_fine=64, perturb=True, noise_std=0.1)
+    ta, tb = trainer(), trainer()
+    per = n // world
+    losses = []
+    for it in range(3):
+        torch.manual_seed(77 + it)
+        noise = ta._draw_noise(n)  # one global draw, sliced per rank: the sharded run sees exactly the single-process noise
+        la = ta.step(ro_f, rd_f, tgt, fr["expr"].to(dev), 2, background=bg[sel], noise=noise).clone()
+        sl = slice(rank * per, (rank + 1) * per)
+        lb = tb.step(ro_f[sl], rd_f[sl], tgt[sl], fr["expr"].to(dev), 2, background=bg[sel][sl],
+                     noise={k: (v[sl] if v is not None else None) for k, v in noise.items()}, world=world, n_total=n).clone()
+        dist.all_reduce(lb)
+        losses.append((la, lb))
+        if it == 0:  # one optimizer step from identical state: every parameter agrees (later steps: see test_fused_train_gpu.py on
+            d = (ta.params - tb.params).abs()  # why Adam at |g| < eps makes longer element-wise comparisons meaningless)
+            assert float(d.max()) <= 1e-6, float(d.max())
+    for la, lb in losses:
+        assert float((la - lb).abs().max()) < 2e-6, (la, lb)
+    chk = tb.params.clone()
+    dist.broadcast(chk, 0)
+    assert torch.equal(chk, tb.params)  # every rank holds the same parameters after the sharded steps
+    ok("fused_trainer_sharded")
+
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

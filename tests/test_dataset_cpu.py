@@ -40,9 +40,40 @@ def test_round_trip_through_load_flame_data(tmp_path, built_lib):
     r = poses[:, :3, :3]
     assert torch.allclose(r @ r.transpose(1, 2), torch.eye(3).expand(n, 3, 3), atol=1e-5)
     assert torch.allclose(poses[:, :3, 3].norm(dim=1), torch.full((n,), 0.5), atol=1e-6)
-    # test=True: poses / expressions of the test split only, no images
+    # test=True: the test split only (images included, as the reference returns them)
     imgs_t, poses_t, _, hwk_t, i_t, exprs_t, _, _ = nerf.load_flame_data(str(tmp_path), test=True)
-    assert imgs_t is None and poses_t.shape == (4, 4, 4) and exprs_t.shape == (4, 76) and hwk_t[:2] == [16, 16]
+    assert imgs_t.shape == (4, 16, 16, 3) and poses_t.shape == (4, 4, 4) and exprs_t.shape == (4, 76) and hwk_t[:2] == [16, 16]
     # half resolution halves the focal lengths and the images
     imgs_h, _, _, hwk_h, _, _, _, _ = nerf.load_flame_data(str(tmp_path), half_res=True)
     assert imgs_h.shape == (n, 8, 8, 3) and np.allclose(hwk_h[2][:2], np.array(info["intrinsics"][:2]) * 0.5)
+
+
+def test_loader_matches_the_reference_loader(tmp_path, built_lib):
+    """nerf.load_flame_data against the UNMODIFIED reference loader (nerf/load_flame.py:40-211, staged copy / live tree) on the
+    same synthetic dataset: every returned member equal, for the train and the test-only call, with and without half_res."""
+    import sys
+
+    import cv2
+    import numpy as np
+    import torch
+
+    import ref_loader
+    ref = ref_loader.load_reference()
+    if ref is None:
+        import pytest
+        pytest.skip("no reference tree (baseline/_ref not staged)")
+    sys.modules["imageio"].imread = lambda p: cv2.imread(p, cv2.IMREAD_UNCHANGED)[..., ::-1]
+    import nerf
+    _writer().write_dataset(str(tmp_path), 32, 3, 1, 4)
+    for kw in (dict(half_res=False, testskip=1, test=True), dict(half_res=True, testskip=1), dict(half_res=False, testskip=2)):
+        a, b = ref.load_flame_data(str(tmp_path), **kw), nerf.load_flame_data(str(tmp_path), **kw)
+        assert len(a) == len(b) == 8
+        for x, y in zip(a, b):
+            if torch.is_tensor(x):
+                assert x.shape == y.shape and float((x.float() - y.float()).abs().max()) == 0.0
+            elif isinstance(x, list) and len(x) == 3 and not isinstance(x[0], np.ndarray):
+                assert x[0] == y[0] and x[1] == y[1] and np.array_equal(np.asarray(x[2]), np.asarray(y[2]))
+            elif isinstance(x, list):
+                assert all(np.array_equal(p, q) for p, q in zip(x, y))
+            else:
+                assert x is None and y is None
