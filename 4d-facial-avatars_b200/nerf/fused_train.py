@@ -87,12 +87,12 @@ class FusedTrainer:
                 out["n_f"] = torch.randn((n, nc + nf), **kw)
         return out if (o["perturb"] or o["noise_std"] > 0.0) else None
 
-    def step(self, ray_origins, ray_directions, target, expressions, latent_index, background=None, world=1, n_total=None,
-             noise=None, events=None, group=None):
-        """One optimizer step on this rank's rays ([n,3] CUDA tensors).  world > 1: the rays are one of `world` equal shards of a
-        batch of n_total rays; the flat gradient bucket is SUM-all-reduced before the update (every rank ends with identical
-        parameters).  Returns the device tensor [mse_coarse, mse_fine] of THIS shard's share (sum over ranks = batch loss).
-        `events`: optional (before_collective, after_collective) CUDA events."""
+    def gradients(self, ray_origins, ray_directions, target, expressions, latent_index, background=None, world=1, n_total=None,
+                  noise=None, events=None, group=None):
+        """Forward, loss and backward of this rank's rays ([n,3] CUDA tensors) into the flat gradient bucket; world > 1: the rays
+        are one of `world` equal shards of a batch of n_total rays and the bucket is SUM-all-reduced (one collective), after
+        which every rank holds the whole batch's gradient.  Returns the device tensor [mse_coarse, mse_fine] of THIS shard's
+        share (sum over ranks = batch loss).  `events`: optional (before_collective, after_collective) CUDA events."""
         eng, o = self.eng, self.opts
         n = ray_origins.shape[0]
         n_total = n * world if n_total is None else n_total
@@ -118,9 +118,20 @@ class FusedTrainer:
             dist.all_reduce(self.grads, group=group)  # ONE collective over the flat bucket (sum: the loss is pre-divided by n_total)
         if events is not None:
             events[1].record()
+        self._reg_row = latent_index
+        return self.loss[:2]
+
+    def update(self):
+        """Adam over the bucket (+ the latent regulariser's gradient on the last frame's row, + zero_grad), then the re-pack."""
+        eng = self.eng
         self.iter += 1
         eng.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.lr(), self.iter, self.betas, self.eps,
-                      reg_offset=self.lat_off + 32 * latent_index if self.latent_reg > 0.0 else -1, reg_weight=self.latent_reg)
+                      reg_offset=self.lat_off + 32 * self._reg_row if self.latent_reg > 0.0 else -1, reg_weight=self.latent_reg)
         eng.repack(self._pc, self._pf)
         eng.mark_synced(self.mc, self.mf)
-        return self.loss[:2]
+
+    def step(self, *args, **kwargs):
+        """One optimizer step: gradients(...) then update().  Returns gradients()'s loss tensor."""
+        loss = self.gradients(*args, **kwargs)
+        self.update()
+        return loss

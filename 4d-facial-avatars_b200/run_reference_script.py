@@ -88,7 +88,8 @@ def _enable_data_parallel():
     def _avg_grads(optimizer, args, kwargs):
         params = [p for g in optimizer.param_groups for p in g["params"]]
         parallel.allreduce_gradients(params, average=True)
-    torch.optim.optimizer.register_optimizer_step_pre_hook(_avg_grads)
+    from torch.optim.optimizer import register_optimizer_step_pre_hook
+    register_optimizer_step_pre_hook(_avg_grads)
     if rank != 0:  # only rank 0 writes files
         import imageio
         imageio.imwrite = imageio.imsave = lambda *a, **k: None

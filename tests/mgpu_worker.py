@@ -93,21 +93,25 @@ def main():
                                         n_latent=4, num_coarse=64, num_fine=64, perturb=True, noise_std=0.1)
     ta, tb = trainer(), trainer()
     per = n // world
-    losses = []
+    sl = slice(rank * per, (rank + 1) * per)
     for it in range(3):
         torch.manual_seed(77 + it)
         noise = ta._draw_noise(n)  # one global draw, sliced per rank: the sharded run sees exactly the single-process noise
-        la = ta.step(ro_f, rd_f, tgt, fr["expr"].to(dev), 2, background=bg[sel], noise=noise).clone()
-        sl = slice(rank * per, (rank + 1) * per)
-        lb = tb.step(ro_f[sl], rd_f[sl], tgt[sl], fr["expr"].to(dev), 2, background=bg[sel][sl],
-                     noise={k: (v[sl] if v is not None else None) for k, v in noise.items()}, world=world, n_total=n).clone()
+        la = ta.gradients(ro_f, rd_f, tgt, fr["expr"].to(dev), 2, background=bg[sel], noise=noise).clone()
+        lb = tb.gradients(ro_f[sl], rd_f[sl], tgt[sl], fr["expr"].to(dev), 2, background=bg[sel][sl],
+                          noise={k: (v[sl] if v is not None else None) for k, v in noise.items()}, world=world, n_total=n).clone()
         dist.all_reduce(lb)
-        losses.append((la, lb))
-        if it == 0:  # one optimizer step from identical state: every parameter agrees (later steps: see test_fused_train_gpu.py on
-            d = (ta.params - tb.params).abs()  # why Adam at |g| < eps makes longer element-wise comparisons meaningless)
-            assert float(d.max()) <= 1e-6, float(d.max())
-    for la, lb in losses:
         assert float((la - lb).abs().max()) < 2e-6, (la, lb)
+        # the all-reduced bucket is the whole batch's gradient.  Tolerance: the gradients travel as FP16 tensor-core operands under
+        # a power-of-two loss scale taken from the rays of the call, so a shard quantises differently from the whole batch:
+        # 3e-3 of each tensor's largest entry, the bound test_train_gpu.py holds the backward itself to (typical: 3e-4).
+        for gview_a, gview_b in zip(ta._gviews, tb._gviews):
+            m = float(gview_a.abs().max())
+            assert float((gview_a - gview_b).abs().max()) <= 3e-3 * max(m, 1e-12), (float((gview_a - gview_b).abs().max()), m)
+        tb.grads.copy_(ta.grads)  # keep the two trainers on one trajectory: this check is about the collective, not about Adam
+        ta.update()
+        tb.update()
+        assert torch.equal(ta.params, tb.params)
     chk = tb.params.clone()
     dist.broadcast(chk, 0)
     assert torch.equal(chk, tb.params)  # every rank holds the same parameters after the sharded steps

@@ -33,14 +33,15 @@ def env(built_lib):
 def tolerance(precision, stress, name):
     """Gate per output.  exact: 1e-4 everywhere, except disp (=1/depth, values ~1-5) on the opaque-stress
     weights where FP32 itself moves by ~1e-4 with the GEMM blocking (see make_golden notes) -> 5e-4.
-    fast (FP16 operands): 1e-4 on random-init weights; opaque-stress is gated by PSNR elsewhere, here loosely."""
+    fast (FP16 operands): 1e-4 on random-init weights; on opaque-stress weights 4e-3 (rgb, acc, w_last) and 4e-2 (disp, values
+    1..5) — measured 1.4e-3 / 1.6e-2; tests/test_parity_gpu.py adds the PSNR gate (>= 68 dB) on the same cases."""
     if precision == "exact":
         if stress:
             return 2e-3 if name.startswith("disp") else 3e-4
         return 1e-4
     if not stress:
         return 1e-4
-    return 8e-2 if name.startswith("disp") else 1e-2
+    return 4e-2 if name.startswith("disp") else 4e-3
 
 
 @pytest.mark.parametrize("precision", ["exact", "fast"])
