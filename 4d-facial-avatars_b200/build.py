@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libnfb.so")
-SOURCES = ["nfb_api.cu", "nfb_pack.cu", "nfb_optim.cu", "nfb_render.cu", "nfb_render2.cu", "nfb_render3.cu", "nfb_train.cu"]
-HEADERS = ["nfb_internal.h", "nfb_layout.h", "nfb_ptx.cuh", "nfb_save.cuh", "nfb_render_common.cuh", "nfb_tile2.cuh", os.path.join("..", "..", "include", "nfb.h")]
+SOURCES = ["nfb_api.cu", "nfb_pack.cu", "nfb_optim.cu", "nfb_post.cu", "nfb_render.cu", "nfb_render2.cu", "nfb_render3.cu", "nfb_train.cu"]
+HEADERS = ["nfb_internal.h", "nfb_layout.h", "nfb_ptx.cuh", "nfb_save.cuh", "nfb_render_common.cuh", "nfb_tile2.cuh", "nfb_sampler.h", os.path.join("..", "..", "include", "nfb.h")]
 
 
 def _nvcc():

@@ -58,6 +58,9 @@ struct NfbHandle {
     bool valid = false;
   } tr;
   float* cond = nullptr;  // [108] = [expression / 3 ; latent] of the current frame
+  // scratch of the steps either side of the path
+  uint32_t* minmax = nullptr;                           // disparity-image min / max keys
+  nfb::smp::Run* smp_runs = nullptr; nfb::smp::Seg* smp_segs = nullptr; int* smp_first = nullptr; long long smp_first_n = 0;
 };
 
 namespace {
@@ -160,6 +163,7 @@ int nfb_destroy(NfbHandle* h) {
   }
   cudaFree(h->tr.rec); cudaFree(h->tr.draw); cudaFree(h->tr.z_c); cudaFree(h->tr.raw_c); cudaFree(h->tr.z_f); cudaFree(h->tr.raw_f);
   cudaFree(h->tr.dnorm); cudaFree(h->tr.scal); cudaFree(h->tr.cond); cudaFree(h->cond);
+  cudaFree(h->minmax); cudaFree(h->smp_runs); cudaFree(h->smp_segs); cudaFree(h->smp_first);
   cudaFree(h->lin_c); cudaFree(h->lin_f); cudaFree(h->d_expr); cudaFree(h->d_latent); cudaFree(h->d_bg); cudaFree(h->d_out);
   delete h;
   return NFB_OK;
@@ -455,6 +459,77 @@ int nfb_render_frame_host(NfbHandle* h, const float pose[12], const double intri
   if (rc) return rc;
   NFB_CUDA(cudaMemcpyAsync(out_host, h->d_out, 11 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
   NFB_CUDA(cudaStreamSynchronize(st));
+  return NFB_OK;
+}
+
+int nfb_frame_products(NfbHandle* h, const float* rgb, const float* disparity, const float* w_last, const double intrinsics[4], int height,
+                       int width, uint8_t* rgb_u8, uint8_t* normals_u8, uint8_t* disparity_u8, void* stream) {
+  if (!h || !intrinsics || height < 2 || width < 2) return NFB_ERR_INVALID;
+  if ((rgb_u8 && !rgb) || ((normals_u8 || disparity_u8) && !disparity)) return NFB_ERR_INVALID;
+  if (normals_u8 && height != width) return NFB_ERR_UNSUPPORTED;  // the reference's expression only broadcasts for square frames
+  NFB_CUDA(cudaSetDevice(h->device));
+  if (!h->minmax) NFB_CUDA(dev_alloc(&h->minmax, 2));
+  NFB_CUDA(nfb::launch_frame_products(rgb, disparity, w_last, intrinsics, height, width, rgb_u8, normals_u8, disparity_u8, h->minmax,
+                                      static_cast<cudaStream_t>(stream), &h->launches));
+  return NFB_OK;
+}
+
+int nfb_sample_rays(NfbHandle* h, const NfbRayMap* map, const double* draws, int size, int max_rounds, long long* indices, int32_t* state,
+                    const NfbRayGather* g, void* stream) {
+  if (!h || !map || !draws || !indices || !state || size < 1 || size > nfb::kSmpMax || max_rounds < 1) return NFB_ERR_INVALID;
+  if (map->height < 1 || map->width < 1 || (long long)map->height * map->width < size) return NFB_ERR_INVALID;
+  if (map->bbox[0] < 0 || map->bbox[1] > map->height || map->bbox[2] < 0 || map->bbox[3] > map->width) return NFB_ERR_INVALID;
+  if (!(map->q_out > 0.0) || !(map->q_in > 0.0)) return NFB_ERR_INVALID;
+  if (1 + 2 * (map->bbox[1] - map->bbox[0]) > nfb::smp::kMaxRuns) return NFB_ERR_UNSUPPORTED;
+  NFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long N = (long long)map->height * map->width;
+  if (!h->smp_runs) NFB_CUDA(dev_alloc(&h->smp_runs, nfb::smp::kMaxRuns));
+  if (!h->smp_segs) NFB_CUDA(dev_alloc(&h->smp_segs, nfb::smp::kMaxSegs));
+  if (h->smp_first_n < N) {
+    if (h->smp_first) NFB_CUDA(cudaFree(h->smp_first));
+    h->smp_first = nullptr; h->smp_first_n = 0;
+    NFB_CUDA(dev_alloc(&h->smp_first, (size_t)N));
+    h->smp_first_n = N;
+    NFB_CUDA(nfb::launch_fill_int(h->smp_first, N, 0x7FFFFFFF, st, &h->launches));
+  }
+  nfb::SampleArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.map.H = map->height; a.map.W = map->width;
+  a.map.b0 = map->bbox[0]; a.map.b1 = map->bbox[1]; a.map.b2 = map->bbox[2]; a.map.b3 = map->bbox[3];
+  a.map.q_out = map->q_out; a.map.q_in = map->q_in;
+  a.draws = draws; a.size = size; a.max_rounds = max_rounds; a.found = indices; a.state = state;
+  a.runs = h->smp_runs; a.segs = h->smp_segs; a.first_pos = h->smp_first;
+  if (g) {
+    if ((g->target && !g->image) || (g->background_out && !g->background) || (g->ray_origins && !g->ray_directions)) return NFB_ERR_INVALID;
+    for (int i = 0; i < 12; ++i) a.pose[i] = g->pose[i];
+    a.fx = static_cast<float>(g->intrinsics[0]);
+    a.fy = static_cast<float>(g->intrinsics[1]);
+    a.wcx = static_cast<float>(static_cast<double>(map->width) * g->intrinsics[2]);
+    a.hcy = static_cast<float>(static_cast<double>(map->height) * g->intrinsics[3]);
+    a.image = g->image; a.background = g->background; a.ray_o = g->ray_origins; a.ray_d = g->ray_directions;
+    a.target = g->target; a.bg_out = g->background_out; a.pixel_rc = g->pixel_rc;
+  }
+  NFB_CUDA(nfb::launch_sample_rays(a, st, &h->launches));
+  return NFB_OK;
+}
+
+int nfb_host_map_cdf(const NfbRayMap* map, const long long* zeroed_sorted, int n_zero, const long long* ks, int n, double* out) {
+  if (!map || !ks || !out || n < 0 || n_zero < 0 || (n_zero && !zeroed_sorted)) return NFB_ERR_INVALID;
+  nfb::smp::Map m;
+  m.H = map->height; m.W = map->width; m.b0 = map->bbox[0]; m.b1 = map->bbox[1]; m.b2 = map->bbox[2]; m.b3 = map->bbox[3];
+  m.q_out = map->q_out; m.q_in = map->q_in;
+  if (nfb::smp::num_runs(m) > nfb::smp::kMaxRuns) return NFB_ERR_UNSUPPORTED;
+  std::vector<nfb::smp::Run> runs(nfb::smp::kMaxRuns);
+  std::vector<nfb::smp::Seg> segs(nfb::smp::kMaxSegs);
+  int nr = 0, ns = 0;
+  const double total = nfb::smp::build_tables(m, zeroed_sorted, n_zero, runs.data(), nr, segs.data(), ns);
+  if (ns > nfb::smp::kMaxSegs) return NFB_ERR_UNSUPPORTED;
+  const long long N = (long long)m.H * m.W;
+  for (int i = 0; i < n; ++i) {
+    if (ks[i] < -1 || ks[i] >= N) return NFB_ERR_INVALID;
+    out[i] = ks[i] < 0 ? total : nfb::smp::cdf_at(ks[i], runs.data(), nr, segs.data(), zeroed_sorted, n_zero);
+  }
   return NFB_OK;
 }
 

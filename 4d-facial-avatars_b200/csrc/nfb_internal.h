@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "nfb_sampler.h"
+
 namespace nfb {
 
 // Device buffers of one loaded network.
@@ -117,5 +119,31 @@ cudaError_t launch_render2(const RenderParams& p, int num_sms, cudaStream_t st, 
 cudaError_t render3_kernel_setup();
 bool render3_supports(const RenderParams& p);
 cudaError_t launch_render3(const RenderParams& p, int num_sms, cudaStream_t st, long long* launches);
+
+// ---- either side of the path (nfb_post.cu)
+cudaError_t launch_frame_products(const float* rgb, const float* disp, const float* w_last, const double intr[4], int H, int W,
+                                  uint8_t* rgb_u8, uint8_t* normals_u8, uint8_t* disp_u8, uint32_t* minmax_scratch, cudaStream_t st,
+                                  long long* launches);
+constexpr int kSmpMax = 2048;  // rays per sampler call (num_random_rays of the shipped YAML)
+struct SampleArgs {
+  smp::Map map;
+  const double* draws;   // uniform [0,1) doubles, consumed like RandomState.rand: round r takes (size - n_found) values
+  int size, max_rounds;
+  long long* found;      // [size] selected flat indices in selection order (= np.random.choice's return value)
+  int* state;            // [0] n_found, [1] rounds run, [2] draws consumed  (in/out: a call may resume a partial selection)
+  smp::Run* runs;
+  smp::Seg* segs;
+  int* first_pos;        // [H * W] scratch, all INT_MAX between calls
+  // gathers (any output may be null)
+  float pose[12];
+  float fx, fy, wcx, hcy;
+  const float* image;       // [H, W, 3]
+  const float* background;  // [H, W, 3]
+  float *ray_o, *ray_d, *target, *bg_out;  // [size, 3] each
+  int* pixel_rc;            // [size, 2] (row, col) of the selected pixels
+};
+
+cudaError_t launch_sample_rays(const SampleArgs& a, cudaStream_t st, long long* launches);
+cudaError_t launch_fill_int(int* p, long long n, int v, cudaStream_t st, long long* launches);
 
 }  // namespace nfb

@@ -13,7 +13,7 @@ NFB_PREC_FAST, NFB_PREC_EXACT = 0, 1
 EXPORTS = ["nfb_version", "nfb_strerror", "nfb_last_cuda_error", "nfb_create", "nfb_destroy", "nfb_load_weights",
            "nfb_set_frame", "nfb_render_forward", "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace",
            "nfb_render_forward_train", "nfb_render_backward", "nfb_train_debug", "nfb_debug_schedule", "nfb_loss_mse_grad",
-           "nfb_adam_step", "nfb_repack"]
+           "nfb_adam_step", "nfb_repack", "nfb_frame_products", "nfb_sample_rays", "nfb_host_map_cdf"]
 
 
 class NfbModelDims(C.Structure):
@@ -64,6 +64,16 @@ class NfbAdam(C.Structure):
                 ("grad_scale", C.c_float), ("reg_offset", C.c_longlong), ("reg_weight", C.c_float)]
 
 
+class NfbRayMap(C.Structure):
+    _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("bbox", C.c_int32 * 4), ("q_out", C.c_double), ("q_in", C.c_double)]
+
+
+class NfbRayGather(C.Structure):
+    _fields_ = [("pose", C.c_float * 12), ("intrinsics", C.c_double * 4), ("image", C.c_void_p), ("background", C.c_void_p),
+                ("ray_origins", C.c_void_p), ("ray_directions", C.c_void_p), ("target", C.c_void_p), ("background_out", C.c_void_p),
+                ("pixel_rc", C.c_void_p)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} not found: build it with `python 4d-facial-avatars_b200/build.py` "
@@ -91,11 +101,18 @@ def _load():
                                       C.c_void_p, C.c_void_p]
     lib.nfb_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(NfbAdam), C.c_void_p]
     lib.nfb_repack.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
+    lib.nfb_frame_products.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.nfb_sample_rays.argtypes = [C.c_void_p, C.POINTER(NfbRayMap), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.POINTER(NfbRayGather), C.c_void_p]
+    lib.nfb_host_map_cdf.argtypes = [C.POINTER(NfbRayMap), C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_longlong), C.c_int,
+                                     C.POINTER(C.c_double)]
     lib.nfb_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     lib.nfb_host_linspace.argtypes = [C.POINTER(C.c_float), C.c_int]
     for fn in ("nfb_create", "nfb_destroy", "nfb_load_weights", "nfb_set_frame", "nfb_render_forward",
                "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace", "nfb_render_forward_train",
-               "nfb_render_backward", "nfb_train_debug", "nfb_loss_mse_grad", "nfb_adam_step", "nfb_repack"):
+               "nfb_render_backward", "nfb_train_debug", "nfb_loss_mse_grad", "nfb_adam_step", "nfb_repack", "nfb_frame_products",
+               "nfb_sample_rays", "nfb_host_map_cdf"):
         getattr(lib, fn).restype = C.c_int
     return lib
 

@@ -216,6 +216,48 @@ int nfb_adam_step(NfbHandle* h, float* params, float* grads, float* exp_avg, flo
 /* nfb_load_weights for both networks in ONE launch (params_fine may be NULL): the re-pack after an optimizer step. */
 int nfb_repack(NfbHandle* h, const float* const params_coarse[26], const float* const params_fine[26], void* stream);
 
+/* ---- The steps either side of the path ----
+ *
+ * nfb_frame_products: the 8-bit images eval_transformed_rays.py writes per rendered frame, from the path's outputs still on the
+ * device: rgb_u8 = cast_to_image(rgb) (:184-192), normals_u8 [(H-1),(W-1),3] = torch_normal_map(disparity, intrinsics, w_last,
+ * clean=True) (:84-119, called at :469 with disp_fine and weights_fine[:, -1]), disparity_u8 = cast_to_disparity_image (:195-198).
+ * Any output (and w_last) may be NULL.  The bytes equal the reference functions' (same FP32 operation order).  Square frames
+ * only for the normal map (the reference's expression does not broadcast otherwise).  1 launch (+1 for disparity_u8). */
+int nfb_frame_products(NfbHandle* h, const float* rgb /* [H,W,3] */, const float* disparity /* [H,W] */,
+                       const float* w_last /* [H,W] or NULL */, const double intrinsics[4], int height, int width, uint8_t* rgb_u8,
+                       uint8_t* normals_u8, uint8_t* disparity_u8, void* stream);
+
+/* Importance map of one training image (train_transformed_rays.py:230-239): probs[bbox[0]:bbox[1], bbox[2]:bbox[3]] = p, 1 - p
+ * elsewhere, normalised; q_out / q_in are the two float64 values of the normalised map exactly as numpy produced them. */
+typedef struct {
+  int32_t height, width;
+  int32_t bbox[4];
+  double q_out, q_in;
+} NfbRayMap;
+/* Optional gathers of nfb_sample_rays (train_transformed_rays.py:323-331); every member may be NULL / unused.  Pixel of flat
+ * index k: (row, col) = (k % height, k / height) — the reference's transposed-meshgrid indexing. */
+typedef struct {
+  float pose[12];            /* camera-to-world 3x4 of the frame: rays as get_ray_bundle would give them */
+  double intrinsics[4];
+  const float* image;        /* [H,W,3] device */
+  const float* background;   /* [H,W,3] device */
+  float* ray_origins;        /* [size,3] out */
+  float* ray_directions;     /* [size,3] out */
+  float* target;             /* [size,3] out */
+  float* background_out;     /* [size,3] out */
+  int32_t* pixel_rc;         /* [size,2] out */
+} NfbRayGather;
+/* np.random.choice(H * W, size, replace=False, p=map.reshape(-1)) (:319-321) on the device, bit-identical indices for the same
+ * uniform draws: `draws` (device, float64 in [0,1)) is consumed exactly like RandomState.rand inside choice — round r reads
+ * (size - n_found) values.  state (device int32[3] = n_found, rounds run, draws consumed; zero it to start) lets a caller that must
+ * stay in lock-step with a host RNG run one round per call.  indices [size] receives the selection in numpy's order; size <= 2048.
+ * 1 launch (one thread block; the float64 cumulative sum is evaluated exactly without being materialised, csrc/nfb_sampler.h). */
+int nfb_sample_rays(NfbHandle* h, const NfbRayMap* map, const double* draws, int size, int max_rounds, long long* indices,
+                    int32_t* state, const NfbRayGather* gather /* nullable */, void* stream);
+/* Host-only test hook of the same arithmetic: out[i] = np.cumsum(p)[ks[i]] (ks[i] == -1: the last entry) for the map with the
+ * ascending flat indices zeroed_sorted set to zero.  No CUDA call. */
+int nfb_host_map_cdf(const NfbRayMap* map, const long long* zeroed_sorted, int n_zero, const long long* ks, int n, double* out);
+
 /* Test hook: device pointers of the training state (valid until the next forward_train on the handle). */
 typedef struct {
   const uint8_t* records;      /* n_tiles records of record_bytes (layout: nfb_layout.h kRec*) */

@@ -100,3 +100,51 @@ def reference_renderer(ref, frame, params_c, params_f, H, W, rows, cols, nc, nf,
                                             encode_position_fn=enc_xyz, encode_direction_fn=enc_dir, expressions=expr,
                                             background_prior=bg, latent_code=latent)
     return run, h * w
+
+
+def load_eval_script(name="eval_transformed_rays.py"):
+    """The reference's eval script as a module WITHOUT running main(): gives tests the unmodified post-render functions
+    (torch_normal_map :84-119, cast_to_image :184-192, cast_to_disparity_image :195-198).  matplotlib / imageio get inert
+    stand-ins when absent; `from nerf import ...` inside the script resolves to the reference package for the import only."""
+    key = "nerf_reference_eval_script"
+    if key in sys.modules:
+        return sys.modules[key]
+    ref = load_reference()
+    path = script_path(name)
+    if ref is None or not path or not os.path.exists(path):
+        return None
+
+    class _Anything:
+        def __call__(self, *a, **k):
+            return self
+
+        def __getattr__(self, n):
+            return self
+    try:
+        import matplotlib  # noqa: F401
+        import matplotlib.pyplot  # noqa: F401
+    except ImportError:
+        anything = _Anything()
+
+        def _attr(n):
+            if n.startswith("__"):
+                raise AttributeError(n)
+            return anything
+        mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+        mpl.__getattr__ = _attr
+        plt.__getattr__ = _attr
+        mpl.pyplot = plt
+        sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
+    saved = sys.modules.get("nerf")
+    sys.modules["nerf"] = ref
+    try:
+        spec = importlib.util.spec_from_file_location(key, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)  # top level only defines functions; main() is behind __name__ == "__main__"
+    finally:
+        if saved is not None:
+            sys.modules["nerf"] = saved
+        else:
+            del sys.modules["nerf"]
+    sys.modules[key] = mod
+    return mod
