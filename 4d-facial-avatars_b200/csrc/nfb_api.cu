@@ -463,14 +463,14 @@ int nfb_render_frame_host(NfbHandle* h, const float pose[12], const double intri
 }
 
 int nfb_frame_products(NfbHandle* h, const float* rgb, const float* disparity, const float* w_last, const double intrinsics[4], int height,
-                       int width, uint8_t* rgb_u8, uint8_t* normals_u8, uint8_t* disparity_u8, void* stream) {
+                       int width, uint8_t* rgb_u8, uint8_t* normals_u8, uint8_t* disparity_u8, int flags, void* stream) {
   if (!h || !intrinsics || height < 2 || width < 2) return NFB_ERR_INVALID;
   if ((rgb_u8 && !rgb) || ((normals_u8 || disparity_u8) && !disparity)) return NFB_ERR_INVALID;
   if (normals_u8 && height != width) return NFB_ERR_UNSUPPORTED;  // the reference's expression only broadcasts for square frames
   NFB_CUDA(cudaSetDevice(h->device));
   if (!h->minmax) NFB_CUDA(dev_alloc(&h->minmax, 2));
   NFB_CUDA(nfb::launch_frame_products(rgb, disparity, w_last, intrinsics, height, width, rgb_u8, normals_u8, disparity_u8, h->minmax,
-                                      static_cast<cudaStream_t>(stream), &h->launches));
+                                      (flags & NFB_PRODUCTS_LIKE_TORCH_CPU) ? 1 : 0, static_cast<cudaStream_t>(stream), &h->launches));
   return NFB_OK;
 }
 

@@ -122,8 +122,8 @@ cudaError_t launch_render3(const RenderParams& p, int num_sms, cudaStream_t st, 
 
 // ---- either side of the path (nfb_post.cu)
 cudaError_t launch_frame_products(const float* rgb, const float* disp, const float* w_last, const double intr[4], int H, int W,
-                                  uint8_t* rgb_u8, uint8_t* normals_u8, uint8_t* disp_u8, uint32_t* minmax_scratch, cudaStream_t st,
-                                  long long* launches);
+                                  uint8_t* rgb_u8, uint8_t* normals_u8, uint8_t* disp_u8, uint32_t* minmax_scratch, int like_torch_cpu,
+                                  cudaStream_t st, long long* launches);
 constexpr int kSmpMax = 2048;  // rays per sampler call (num_random_rays of the shipped YAML)
 struct SampleArgs {
   smp::Map map;

@@ -4,8 +4,8 @@
 //     clamp, x255, truncate), torch_normal_map (:84-119: back-project the disparity map, cross product of the forward differences,
 //     normalise, x0.5+0.5, clean with the last-sample weights: > 0.22 -> 1 and a (1-w) n + w blend, x255, truncate) and
 //     cast_to_disparity_image (:195-198: min/max normalise).  The FP32 operation order of the torch expressions is kept (every
-//     torch op rounds once; torch.cross contracts a1*b2 - a2*b1 into fma(a1, b2, -(a2*b1)) on both of its back ends), so the bytes
-//     equal the reference function's.
+//     torch op rounds once; torch.cross contracts a1*b2 - a2*b1 into fma(a1, b2, -(a2*b1)) on both of its back ends; torch's CPU
+//     and CUDA back ends differ in two roundings — selectable, see ProductArgs), so the bytes equal the reference function's.
 //   * ray sampler (before the path): see the second half of this file.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,12 +31,18 @@ struct ProductArgs {
   uint8_t* rgb_u8;      // [H, W, 3] or null
   uint8_t* normals_u8;  // [H - 1, W - 1, 3] or null
   uint32_t* minmax;     // [2] ordered keys of min / max disparity (null: no disparity image requested)
+  // Where torch's two back ends round differently (measured on this image, torch 2.11): the CUDA back end divides a tensor by a
+  // host scalar as a multiplication by its FP32 reciprocal (".../ fx") and sums the three squared components as (x2 + z2) + y2;
+  // the CPU back end divides and sums (x2 + y2) + z2.
+  int like_cpu;
+  float inv_fx, inv_fy;
 };
 
 // point of pixel (r, c): (((c - cx) * d) / fx, -(((r - cy) * d) / fy), d)
 __device__ __forceinline__ void back_project(const ProductArgs& a, int r, int c, float d, float& x, float& y) {
-  x = __fdiv_rn(__fmul_rn(__fsub_rn((float)c, a.cx), d), a.fx);
-  y = -__fdiv_rn(__fmul_rn(__fsub_rn((float)r, a.cy), d), a.fy);
+  const float u = __fmul_rn(__fsub_rn((float)c, a.cx), d), v = __fmul_rn(__fsub_rn((float)r, a.cy), d);
+  x = a.like_cpu ? __fdiv_rn(u, a.fx) : __fmul_rn(u, a.inv_fx);
+  y = -(a.like_cpu ? __fdiv_rn(v, a.fy) : __fmul_rn(v, a.inv_fy));
 }
 __device__ __forceinline__ float cross_term(float a1, float b2, float a2, float b1) { return __fmaf_rn(a1, b2, -__fmul_rn(a2, b1)); }
 __device__ __forceinline__ uint8_t to_u8(float v) {  // numpy astype('uint8') / torch .byte() of a value in [0, 255]: truncate
@@ -70,7 +76,8 @@ __global__ void __launch_bounds__(256) frame_products_kernel(const ProductArgs a
       const float a0 = __fsub_rn(x01, x00), a1 = __fsub_rn(y01, y00), a2 = __fsub_rn(d01, d00);
       const float b0 = __fsub_rn(x10, x00), b1 = __fsub_rn(y10, y00), b2 = __fsub_rn(d10, d00);
       float nrm[3] = {cross_term(a1, b2, a2, b1), cross_term(a2, b0, a0, b2), cross_term(a0, b1, a1, b0)};
-      const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nrm[0], nrm[0]), __fmul_rn(nrm[1], nrm[1])), __fmul_rn(nrm[2], nrm[2])));
+      const float q0 = __fmul_rn(nrm[0], nrm[0]), q1 = __fmul_rn(nrm[1], nrm[1]), q2 = __fmul_rn(nrm[2], nrm[2]);
+      const float len = __fsqrt_rn(a.like_cpu ? __fadd_rn(__fadd_rn(q0, q1), q2) : __fadd_rn(__fadd_rn(q0, q2), q1));
       const float m = a.w_last ? a.w_last[i] : 0.f;
       uint8_t* out = a.normals_u8 + 3 * ((size_t)r * (a.W - 1) + c);
 #pragma unroll
@@ -110,9 +117,12 @@ __global__ void __launch_bounds__(256) disparity_image_kernel(const float* __res
 }
 
 cudaError_t launch_frame_products(const float* rgb, const float* disp, const float* w_last, const double intr[4], int H, int W,
-                                  uint8_t* rgb_u8, uint8_t* normals_u8, uint8_t* disp_u8, uint32_t* minmax_scratch, cudaStream_t st,
-                                  long long* launches) {
+                                  uint8_t* rgb_u8, uint8_t* normals_u8, uint8_t* disp_u8, uint32_t* minmax_scratch, int like_torch_cpu,
+                                  cudaStream_t st, long long* launches) {
   ProductArgs a;
+  a.like_cpu = like_torch_cpu;
+  a.inv_fx = 1.0f / (float)intr[0];
+  a.inv_fy = 1.0f / (float)intr[1];
   a.rgb = rgb; a.disp = disp; a.w_last = w_last; a.H = H; a.W = W;
   a.fx = (float)intr[0]; a.fy = (float)intr[1];
   a.cx = (float)(intr[2] * (double)H);  // the reference multiplies by depthmap.shape[0] for x and shape[1] for y (square frames)

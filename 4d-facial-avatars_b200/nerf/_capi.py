@@ -102,7 +102,7 @@ def _load():
     lib.nfb_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(NfbAdam), C.c_void_p]
     lib.nfb_repack.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
     lib.nfb_frame_products.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_int,
-                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.nfb_sample_rays.argtypes = [C.c_void_p, C.POINTER(NfbRayMap), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.POINTER(NfbRayGather), C.c_void_p]
     lib.nfb_host_map_cdf.argtypes = [C.POINTER(NfbRayMap), C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_longlong), C.c_int,

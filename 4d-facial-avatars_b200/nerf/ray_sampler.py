@@ -86,10 +86,10 @@ class RaySampler:
         return out
 
 
-def frame_products(rgb, disparity, w_last, intrinsics, want_disparity=False):
+def frame_products(rgb, disparity, w_last, intrinsics, want_disparity=False, like_torch_cpu=False):
     """cast_to_image / torch_normal_map(clean=True) / cast_to_disparity_image of eval_transformed_rays.py (:84-119, :184-198) on
     the device, one launch: [H,W,3] rgb, [H,W] disparity and last-sample weights -> uint8 tensors (rgb, normals [(H-1),(W-1),3],
-    optionally the disparity image)."""
+    optionally the disparity image).  like_torch_cpu: round like torch's CPU back end instead of its CUDA back end (include/nfb.h: NFB_PRODUCTS_LIKE_TORCH_CPU)."""
     dev = rgb.device
     eng = _engine.renderer_for(dev)
     H, W = disparity.shape
@@ -100,6 +100,7 @@ def frame_products(rgb, disparity, w_last, intrinsics, want_disparity=False):
     out_d = torch.empty((H, W), dtype=torch.uint8, device=dev) if want_disparity else None
     intr = (C.c_double * 4)(*[float(v) for v in intrinsics])
     capi.check(capi.lib.nfb_frame_products(eng._h, _engine._ptr(rgb), _engine._ptr(disparity), _engine._ptr(w_last), intr, H, W,
-                                           _engine._ptr(out_rgb), _engine._ptr(out_n), _engine._ptr(out_d), _engine._stream()),
+                                           _engine._ptr(out_rgb), _engine._ptr(out_n), _engine._ptr(out_d), 1 if like_torch_cpu else 0,
+                                           _engine._stream()),
                "frame_products")
     return out_rgb, out_n, out_d

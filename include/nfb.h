@@ -221,11 +221,16 @@ int nfb_repack(NfbHandle* h, const float* const params_coarse[26], const float* 
  * nfb_frame_products: the 8-bit images eval_transformed_rays.py writes per rendered frame, from the path's outputs still on the
  * device: rgb_u8 = cast_to_image(rgb) (:184-192), normals_u8 [(H-1),(W-1),3] = torch_normal_map(disparity, intrinsics, w_last,
  * clean=True) (:84-119, called at :469 with disp_fine and weights_fine[:, -1]), disparity_u8 = cast_to_disparity_image (:195-198).
- * Any output (and w_last) may be NULL.  The bytes equal the reference functions' (same FP32 operation order).  Square frames
- * only for the normal map (the reference's expression does not broadcast otherwise).  1 launch (+1 for disparity_u8). */
+ * Any output (and w_last) may be NULL.  The bytes equal the reference functions' (same FP32 operation order).  torch's two back
+ * ends round torch_normal_map differently in two places: CUDA turns ".../ fx" (division by a host scalar) into a multiplication by
+ * the FP32 reciprocal and sums the normal's squared components as (x2 + z2) + y2; the CPU divides and sums (x2 + y2) + z2.  The
+ * default follows the CUDA back end — what the eval script computes on a GPU; NFB_PRODUCTS_LIKE_TORCH_CPU follows the CPU back
+ * end (the two differ by one level in ~2e-4 of the bytes).  Square frames only for the normal map (the reference's expression
+ * does not broadcast otherwise).  1 launch (+1 for disparity_u8). */
+enum { NFB_PRODUCTS_LIKE_TORCH_CPU = 1 };
 int nfb_frame_products(NfbHandle* h, const float* rgb /* [H,W,3] */, const float* disparity /* [H,W] */,
                        const float* w_last /* [H,W] or NULL */, const double intrinsics[4], int height, int width, uint8_t* rgb_u8,
-                       uint8_t* normals_u8, uint8_t* disparity_u8, void* stream);
+                       uint8_t* normals_u8, uint8_t* disparity_u8, int flags, void* stream);
 
 /* Importance map of one training image (train_transformed_rays.py:230-239): probs[bbox[0]:bbox[1], bbox[2]:bbox[3]] = p, 1 - p
  * elsewhere, normalised; q_out / q_in are the two float64 values of the normalised map exactly as numpy produced them. */
