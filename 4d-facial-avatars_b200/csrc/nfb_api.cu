@@ -56,7 +56,14 @@ struct NfbHandle {
     float* cond = nullptr;                              // [108] conditioning vector of the frame the forward rendered
     int n_rays = 0, nc = 0, nf = 0, rays_per_unit = 0, tiles_c = 0, tiles_f = 0, n_units = 0, has_bg = 0, white_bkgd = 0;
     bool valid = false;
+    // chunked mode (the records of the whole call would exceed the memory budget): the forward only produced the outputs; the
+    // backward re-runs the training forward chunk by chunk from the saved launch parameters (the caller keeps the inputs alive)
+    bool chunked = false;
+    nfb::RenderParams full;      // the forward call's parameters (pointers into caller memory)
+    int chunk_rays = 0, precision = 0;
+    float* scratch_out = nullptr; size_t scratch_cap = 0;   // [11 * chunk_rays] outputs of the re-run forwards (discarded)
   } tr;
+  size_t train_budget = 0;       // bytes the per-tile records of one launch may take (0: not decided yet)
   float* cond = nullptr;  // [108] = [expression / 3 ; latent] of the current frame
   // scratch of the steps either side of the path
   uint32_t* minmax = nullptr;                           // disparity-image min / max keys
@@ -162,7 +169,7 @@ int nfb_destroy(NfbHandle* h) {
     cudaFree(h->tr.acc[n]);
   }
   cudaFree(h->tr.rec); cudaFree(h->tr.draw); cudaFree(h->tr.z_c); cudaFree(h->tr.raw_c); cudaFree(h->tr.z_f); cudaFree(h->tr.raw_f);
-  cudaFree(h->tr.dnorm); cudaFree(h->tr.scal); cudaFree(h->tr.cond); cudaFree(h->cond);
+  cudaFree(h->tr.dnorm); cudaFree(h->tr.scal); cudaFree(h->tr.cond); cudaFree(h->tr.scratch_out); cudaFree(h->cond);
   cudaFree(h->minmax); cudaFree(h->smp_runs); cudaFree(h->smp_segs); cudaFree(h->smp_first);
   cudaFree(h->lin_c); cudaFree(h->lin_f); cudaFree(h->d_expr); cudaFree(h->d_latent); cudaFree(h->d_bg); cudaFree(h->d_out);
   delete h;
@@ -244,6 +251,38 @@ static int ensure_linspace(float** buf, int* cached_n, int n, cudaStream_t st) {
   return NFB_OK;
 }
 
+// Memory the per-tile activation records of ONE training launch may take: NFB_TRAIN_MEM_MB, else 60 % of the device memory that
+// is free when first asked (at least 1 GiB).  A call that needs more is processed in ray chunks (see NfbHandle::Train::chunked).
+static size_t train_budget(NfbHandle* h) {
+  if (const char* e = std::getenv("NFB_TRAIN_MEM_MB")) {  // read on every call: tests switch it within one process
+    const size_t mb = (size_t)std::strtoull(e, nullptr, 10);
+    if (mb) return mb << 20;
+  }
+  if (h->train_budget) return h->train_budget;
+  size_t budget = 0;
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = free_b / 10 * 6;
+  }
+  if (budget < ((size_t)1 << 30)) budget = (size_t)1 << 30;
+  return h->train_budget = budget;
+}
+
+// (Re)size the buffers a training launch over n rays / `tiles` tiles writes.
+static int ensure_train_buffers(NfbHandle::Train& tr, size_t n, size_t tiles, int nc, int nf) {
+  int rc;
+  if ((rc = ensure_cap(&tr.rec, &tr.rec_tiles, tiles * nfb::kRecBytes))) return rc;
+  if ((rc = ensure_cap(&tr.draw, &tr.draw_tiles, tiles * 512))) return rc;
+  if ((rc = ensure_cap(&tr.z_c, &tr.cap_zc, n * nc))) return rc;
+  if ((rc = ensure_cap(&tr.raw_c, &tr.cap_rawc, n * nc * 4))) return rc;
+  if ((rc = ensure_cap(&tr.dnorm, &tr.cap_dn, n))) return rc;
+  if (nf > 0) {
+    if ((rc = ensure_cap(&tr.z_f, &tr.cap_zf, n * (nc + nf)))) return rc;
+    if ((rc = ensure_cap(&tr.raw_f, &tr.cap_rawf, n * (nc + nf) * 4))) return rc;
+  }
+  return NFB_OK;
+}
+
 static int render_impl(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm, const NfbNoise* noise, const NfbOutputs* out,
                        const NfbDebug* dbg, void* stream, bool train) {
   if (!h || !rays || !sm || !out) return NFB_ERR_INVALID;
@@ -315,28 +354,34 @@ static int render_impl(NfbHandle* h, const NfbRays* rays, const NfbSampling* sm,
     // Saved for nfb_render_backward: per-tile activation records, sample depths, (colour, ReLU input of sigma), |d|.
     NfbHandle::Train& tr = h->tr;
     tr.valid = false;
-    const size_t n = (size_t)rays->n_rays, tiles = (size_t)p.n_units * (p.tiles_c + p.tiles_f);
+    const size_t n = (size_t)rays->n_rays, tiles_per_unit = (size_t)(p.tiles_c + p.tiles_f), tiles = (size_t)p.n_units * tiles_per_unit;
     int rc;
-    if ((rc = ensure_cap(&tr.rec, &tr.rec_tiles, tiles * nfb::kRecBytes))) return rc;
-    if ((rc = ensure_cap(&tr.draw, &tr.draw_tiles, tiles * 512))) return rc;
-    if ((rc = ensure_cap(&tr.z_c, &tr.cap_zc, n * nc))) return rc;
-    if ((rc = ensure_cap(&tr.raw_c, &tr.cap_rawc, n * nc * 4))) return rc;
-    if ((rc = ensure_cap(&tr.dnorm, &tr.cap_dn, n))) return rc;
-    if (nf > 0) {
-      if ((rc = ensure_cap(&tr.z_f, &tr.cap_zf, n * (nc + nf)))) return rc;
-      if ((rc = ensure_cap(&tr.raw_f, &tr.cap_rawf, n * (nc + nf) * 4))) return rc;
-    }
+    tr.chunked = tiles * nfb::kRecBytes > train_budget(h);
+    if (tr.chunked) {
+      // e.g. a whole frame rendered with gradients enabled: 1.5-2 MiB of records per ray.  Keep the launch parameters, produce
+      // the outputs with the evaluation kernel now, and let the backward re-run the training forward in chunks that fit.
+      if (!rays->o) { g_last_cuda_error = "training forward over budget needs explicit rays (o, d)"; return NFB_ERR_UNSUPPORTED; }
+      size_t units = train_budget(h) / nfb::kRecBytes / tiles_per_unit;
+      units &= ~(size_t)1;  // whole two-tile units of work
+      if (units < 2) units = 2;
+      tr.chunk_rays = (int)(units * p.rays_per_unit);
+      tr.full = p;
+      tr.precision = exact ? 1 : 0;
+    } else if ((rc = ensure_train_buffers(tr, n, tiles, nc, nf))) return rc;
     // a later nfb_set_frame (e.g. a validation render before the backward) must not change what the backward differentiates
     NFB_CUDA(cudaMemcpyAsync(tr.cond, h->cond, nfb::kDimCond * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    p.save_rec = tr.rec; p.save_dnorm = tr.dnorm; p.save_raw_c = tr.raw_c; p.save_raw_f = tr.raw_f;
-    p.dbg_z_c = tr.z_c; p.dbg_z_f = tr.z_f;
+    if (!tr.chunked) {
+      p.save_rec = tr.rec; p.save_dnorm = tr.dnorm; p.save_raw_c = tr.raw_c; p.save_raw_f = tr.raw_f;
+      p.dbg_z_c = tr.z_c; p.dbg_z_f = tr.z_f;
+    }
     tr.n_rays = rays->n_rays; tr.nc = nc; tr.nf = nf; tr.rays_per_unit = p.rays_per_unit; tr.tiles_c = p.tiles_c;
     tr.tiles_f = p.tiles_f; tr.n_units = p.n_units; tr.has_bg = rays->background != nullptr; tr.white_bkgd = p.white_bkgd;
   }
   // fast-mode evaluation runs the two-tiles-in-flight kernel (the training forward only on request, see nfb_create); exact
   // mode (hi+lo operands need twice the TMEM columns) and the layer probe run the one-tile kernel
-  const bool two_tile = h->use_render2 && !exact && !p.dbg_act && (!train || h->train_render2);
-  if (two_tile && !train && h->use_render3 && nfb::render3_supports(p)) NFB_CUDA(nfb::launch_render3(p, h->num_sms, st, &h->launches));
+  const bool saving = train && !h->tr.chunked;
+  const bool two_tile = h->use_render2 && !exact && !p.dbg_act && (!saving || h->train_render2);
+  if (two_tile && !saving && h->use_render3 && nfb::render3_supports(p)) NFB_CUDA(nfb::launch_render3(p, h->num_sms, st, &h->launches));
   else if (two_tile) NFB_CUDA(nfb::launch_render2(p, h->num_sms, st, &h->launches));
   else NFB_CUDA(nfb::launch_render(p, exact ? 1 : 0, h->num_sms, st, &h->launches));
   if (train) h->tr.valid = true;
@@ -367,39 +412,87 @@ int nfb_render_backward(NfbHandle* h, const NfbOutGrads* og, const float* const 
   }
   NFB_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t tiles = (size_t)tr.n_units * (tr.tiles_c + tr.tiles_f);
-  NFB_CUDA(cudaMemsetAsync(tr.draw, 0, tiles * 512 * sizeof(float), st));
   NFB_CUDA(cudaMemsetAsync(tr.acc[0], 0, nfb::kAccFloats * sizeof(float), st));
   NFB_CUDA(cudaMemsetAsync(tr.acc[1], 0, nfb::kAccFloats * sizeof(float), st));
-  NFB_CUDA(cudaMemsetAsync(tr.scal, 0, 4 * sizeof(float), st));
 
-  nfb::CompBwdParams q;
-  std::memset(&q, 0, sizeof(q));
-  q.n_rays = tr.n_rays; q.nc = tr.nc; q.nf = tr.nf; q.s_fine = tr.nc + tr.nf; q.rays_per_unit = tr.rays_per_unit;
-  q.tiles_c = tr.tiles_c; q.tiles_f = tr.tiles_f; q.has_bg = tr.has_bg; q.white_bkgd = tr.white_bkgd;
-  q.z_c = tr.z_c; q.raw_c = tr.raw_c; q.z_f = tr.z_f; q.raw_f = tr.raw_f; q.dnorm = tr.dnorm;
-  q.g_rgb[0] = og->rgb_coarse; q.g_disp[0] = og->disp_coarse; q.g_acc[0] = og->acc_coarse;
-  q.g_rgb[1] = og->rgb_fine; q.g_disp[1] = og->disp_fine; q.g_acc[1] = og->acc_fine; q.g_wlast = og->w_last;
-  q.draw = tr.draw; q.acc[0] = tr.acc[0]; q.acc[1] = tr.acc[1];
-  q.absmax = reinterpret_cast<unsigned int*>(tr.scal + 2);
-  NFB_CUDA(nfb::launch_composite_bwd(q, tr.scal, st, &h->launches));
+  // compositing backward -> dX chain -> weight-gradient GEMMs for the rays [begin, begin + n) whose training state the buffers
+  // hold; the FP32 accumulators tr.acc add up over chunks (each chunk has its own power-of-two loss scale, divided out again
+  // before the accumulation)
+  auto backward_rays = [&](int begin, int n, int n_units) -> int {
+    const size_t tiles = (size_t)n_units * (tr.tiles_c + tr.tiles_f);
+    NFB_CUDA(cudaMemsetAsync(tr.draw, 0, tiles * 512 * sizeof(float), st));
+    NFB_CUDA(cudaMemsetAsync(tr.scal, 0, 4 * sizeof(float), st));
+    nfb::CompBwdParams q;
+    std::memset(&q, 0, sizeof(q));
+    q.n_rays = n; q.nc = tr.nc; q.nf = tr.nf; q.s_fine = tr.nc + tr.nf; q.rays_per_unit = tr.rays_per_unit;
+    q.tiles_c = tr.tiles_c; q.tiles_f = tr.tiles_f; q.has_bg = tr.has_bg; q.white_bkgd = tr.white_bkgd;
+    q.z_c = tr.z_c; q.raw_c = tr.raw_c; q.z_f = tr.z_f; q.raw_f = tr.raw_f; q.dnorm = tr.dnorm;
+    auto off3 = [&](const float* p) { return p ? p + 3 * (size_t)begin : nullptr; };
+    auto off1 = [&](const float* p) { return p ? p + (size_t)begin : nullptr; };
+    q.g_rgb[0] = off3(og->rgb_coarse); q.g_disp[0] = off1(og->disp_coarse); q.g_acc[0] = off1(og->acc_coarse);
+    q.g_rgb[1] = off3(og->rgb_fine); q.g_disp[1] = off1(og->disp_fine); q.g_acc[1] = off1(og->acc_fine); q.g_wlast = off1(og->w_last);
+    q.draw = tr.draw; q.acc[0] = tr.acc[0]; q.acc[1] = tr.acc[1];
+    q.absmax = reinterpret_cast<unsigned int*>(tr.scal + 2);
+    NFB_CUDA(nfb::launch_composite_bwd(q, tr.scal, st, &h->launches));
 
-  nfb::ChainParams c;
-  c.n_units = tr.n_units; c.tiles_c = tr.tiles_c; c.tiles_f = tr.tiles_f;
-  c.rec = tr.rec; c.draw = tr.draw; c.scal = tr.scal;
-  c.wstream[0] = h->net[0].stream_bwd;
-  c.wstream[1] = fine ? h->net[1].stream_bwd : h->net[0].stream_bwd;
-  NFB_CUDA(nfb::launch_chain(c, h->num_sms, st, &h->launches));
+    nfb::ChainParams c;
+    c.n_units = n_units; c.tiles_c = tr.tiles_c; c.tiles_f = tr.tiles_f;
+    c.rec = tr.rec; c.draw = tr.draw; c.scal = tr.scal;
+    c.wstream[0] = h->net[0].stream_bwd;
+    c.wstream[1] = fine ? h->net[1].stream_bwd : h->net[0].stream_bwd;
+    NFB_CUDA(nfb::launch_chain(c, h->num_sms, st, &h->launches));
+    for (int net = 0; net < (fine ? 2 : 1); ++net) {
+      nfb::DwParams d;
+      d.rec = tr.rec; d.n_units = n_units; d.tpu = tr.tiles_c + tr.tiles_f;
+      d.t_base = net ? tr.tiles_c : 0; d.t_cnt = net ? tr.tiles_f : tr.tiles_c;
+      d.acc = tr.acc[net]; d.scal = tr.scal;
+      NFB_CUDA(nfb::launch_dw(d, h->num_sms, st, &h->launches));
+    }
+    return NFB_OK;
+  };
 
-  for (int net = 0; net < (fine ? 2 : 1); ++net) {
-    nfb::DwParams d;
-    d.rec = tr.rec; d.n_units = tr.n_units; d.tpu = tr.tiles_c + tr.tiles_f;
-    d.t_base = net ? tr.tiles_c : 0; d.t_cnt = net ? tr.tiles_f : tr.tiles_c;
-    d.acc = tr.acc[net]; d.scal = tr.scal;
-    NFB_CUDA(nfb::launch_dw(d, h->num_sms, st, &h->launches));
+  if (!tr.chunked) {
+    int rc = backward_rays(0, tr.n_rays, tr.n_units);
+    if (rc) return rc;
+  } else {
+    const int R = tr.rays_per_unit;
+    for (int begin = 0; begin < tr.n_rays; begin += tr.chunk_rays) {
+      const int n = tr.n_rays - begin < tr.chunk_rays ? tr.n_rays - begin : tr.chunk_rays;
+      const int n_units = (n + R - 1) / R;
+      const size_t tiles = (size_t)n_units * (tr.tiles_c + tr.tiles_f);
+      int rc = ensure_train_buffers(tr, (size_t)n, tiles, tr.nc, tr.nf);
+      if (rc) return rc;
+      if (tr.scratch_cap < 11 * (size_t)tr.chunk_rays) {
+        if (tr.scratch_out) NFB_CUDA(cudaFree(tr.scratch_out));
+        tr.scratch_out = nullptr; tr.scratch_cap = 0;
+        NFB_CUDA(dev_alloc(&tr.scratch_out, 11 * (size_t)tr.chunk_rays));
+        tr.scratch_cap = 11 * (size_t)tr.chunk_rays;
+      }
+      // the training forward of this chunk: the saved launch with every per-ray pointer advanced to `begin`
+      nfb::RenderParams p = tr.full;
+      const size_t b = (size_t)begin;
+      p.o += 3 * b; p.d += 3 * b; p.n_rays = n; p.n_units = n_units;
+      if (p.dir_z) p.dir_z += b;
+      if (p.bg) p.bg += 3 * b;
+      if (p.t_rand) p.t_rand += b * tr.nc;
+      if (p.noise_c) p.noise_c += b * tr.nc;
+      if (p.u_rand) p.u_rand += b * tr.nf;
+      if (p.noise_f) p.noise_f += b * (tr.nc + tr.nf);
+      float* so = tr.scratch_out;
+      const size_t cn = (size_t)tr.chunk_rays;
+      p.rgb_c = so; p.disp_c = so + 3 * cn; p.acc_c = so + 4 * cn; p.rgb_f = so + 5 * cn; p.disp_f = so + 8 * cn; p.acc_f = so + 9 * cn;
+      p.w_last = so + 10 * cn;
+      p.save_rec = tr.rec; p.save_dnorm = tr.dnorm; p.save_raw_c = tr.raw_c; p.save_raw_f = tr.raw_f;
+      p.dbg_z_c = tr.z_c; p.dbg_z_f = tr.z_f;
+      if (h->train_render2 && tr.precision == 0) NFB_CUDA(nfb::launch_render2(p, h->num_sms, st, &h->launches));
+      else NFB_CUDA(nfb::launch_render(p, tr.precision, h->num_sms, st, &h->launches));
+      rc = backward_rays(begin, n, n_units);
+      if (rc) return rc;
+    }
+  }
+  for (int net = 0; net < (fine ? 2 : 1); ++net)
     NFB_CUDA(nfb::launch_finalize(net ? params_fine : params_coarse, net ? grads_fine : grads_coarse, tr.acc[net], tr.cond, st,
                                   &h->launches));
-  }
   if (grad_latent)
     NFB_CUDA(nfb::launch_latent_grad(params_coarse, fine ? params_fine : nullptr, tr.acc[0], tr.acc[1], grad_latent, st,
                                      &h->launches));
@@ -408,7 +501,7 @@ int nfb_render_backward(NfbHandle* h, const NfbOutGrads* og, const float* const 
 
 int nfb_train_debug(NfbHandle* h, NfbTrainDebug* out) {
   if (!h || !out) return NFB_ERR_INVALID;
-  if (!h->tr.valid) return NFB_ERR_STATE;
+  if (!h->tr.valid || h->tr.chunked) return NFB_ERR_STATE;  // chunked: the buffers only ever hold one chunk
   const NfbHandle::Train& tr = h->tr;
   out->records = tr.rec; out->n_tiles = (long long)tr.n_units * (tr.tiles_c + tr.tiles_f); out->record_bytes = nfb::kRecBytes;
   out->d_raw = tr.draw; out->acc_coarse = tr.acc[0]; out->acc_fine = tr.acc[1]; out->acc_floats = nfb::kAccFloats;

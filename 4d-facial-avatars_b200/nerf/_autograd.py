@@ -16,6 +16,7 @@ class _RenderFn(torch.autograd.Function):
     def forward(ctx, eng, rays, args, has_fine, expr, latent, *params):
         out = eng.render(rays[:, :3], rays[:, 3:6], train=True, **args)
         ctx.eng = eng
+        ctx.keep = out.get("_keep")  # the chunked backward (include/nfb.h) re-reads the forward's inputs
         ctx.token = eng.train_token
         ctx.has_fine = has_fine
         ctx.latent_shape = latent.shape

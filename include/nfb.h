@@ -161,7 +161,11 @@ int nfb_render_forward(NfbHandle* h, const NfbRays* rays, const NfbSampling* sam
  * nfb_render_forward_train is nfb_render_forward that additionally keeps, in buffers owned by the handle, what the
  * backward needs: per-sample depths, colours and ReLU inputs of both passes, and per 128-row tile the FP16 activations
  * of every layer (about 1 MiB per tile; 2048 rays at 64+64 samples = 3 GiB).  The next nfb_render_backward on the same
- * handle consumes that state; weights must not be re-loaded in between. */
+ * handle consumes that state; weights must not be re-loaded in between.
+ * Memory: when the records of the whole call would exceed the budget (environment NFB_TRAIN_MEM_MB, default 60 % of the free
+ * device memory) — e.g. a full frame rendered with gradients enabled — the forward only renders (evaluation kernel) and the
+ * backward re-runs the training forward chunk by chunk inside the budget: same gradients, one extra forward; the caller must
+ * then keep the forward's input buffers alive until the backward, and explicit rays are required. */
 int nfb_render_forward_train(NfbHandle* h, const NfbRays* rays, const NfbSampling* sampling,
                              const NfbNoise* noise /* nullable */, const NfbOutputs* out, void* stream);
 

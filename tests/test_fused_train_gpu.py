@@ -211,3 +211,39 @@ def test_in_loop_validation_keeps_the_saved_training_state(env):
         grads.append([p.grad.clone() for p in mc.parameters() if p.grad is not None] + [lat.grad.clone()])
     for a, b in zip(*grads):
         assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(a.abs().max()))
+
+
+def test_training_over_the_memory_budget_runs_in_chunks(env, monkeypatch):
+    """a training-mode call whose per-tile records exceed the budget (a full frame with gradients enabled needs
+    hundreds of GiB) must not die in cudaMalloc.  With NFB_TRAIN_MEM_MB=48 a 160-ray batch (64c+64f: 240 tiles = 240 MiB of
+    records) is processed in 5 chunks; outputs are identical and the gradients agree with the one-launch path to the FP16
+    operand precision (each chunk has its own loss scale)."""
+    nerf, _engine, fused_train, dev = env
+    fr, ro, rd, bg, tgt, idx = _batches(dev, 1, 160)
+    sel = idx[0]
+    expr = fr["expr"].to(dev)
+    blk = dict(num_coarse=64, num_fine=64, perturb=True, lindisp=False, radiance_field_noise_std=0.1, white_background=False, chunksize=64)
+    cfg = nerf.CfgNode(dict(nerf=dict(use_viewdirs=True, train=blk), dataset=dict(no_ndc=True, near=0.2, far=0.8)))
+    results = []
+    for budget in (None, "48"):
+        if budget:
+            monkeypatch.setenv("NFB_TRAIN_MEM_MB", budget)
+        mc, mf = make_model(nerf, O.random_init_params(100), dev), make_model(nerf, O.random_init_params(101), dev)
+        lat = torch.full((32,), 0.01, device=dev, requires_grad=True)
+        torch.manual_seed(9)
+        eng = _engine.renderer_for(dev)
+        l0 = eng.launch_count()
+        out = nerf.run_one_iter_of_nerf(32, 32, fr["intrinsics"], mc, mf, ro[sel], rd[sel], cfg, mode="train", expressions=expr,
+                                        background_prior=bg[sel], latent_code=lat)
+        loss = ((out[0] - tgt[sel]) ** 2).mean() + ((out[3] - tgt[sel]) ** 2).mean() + out[6].mean() * 0.1
+        loss.backward()
+        torch.cuda.synchronize()
+        results.append(([o.detach().clone() for o in out], [p.grad.clone() for p in list(mc.parameters()) + list(mf.parameters()) if p.grad is not None] + [lat.grad.clone()],
+                        eng.launch_count() - l0))
+    monkeypatch.delenv("NFB_TRAIN_MEM_MB")
+    (o1, g1, n1), (o2, g2, n2) = results
+    assert n2 > n1 + 10  # several chunks' worth of launches
+    for a, b in zip(o1, o2):
+        assert float((a - b).abs().max()) < 1e-5   # the evaluation kernel renders what the training forward renders
+    for a, b in zip(g1, g2):
+        assert float((a - b).abs().max()) <= 3e-3 * max(float(a.abs().max()), 1e-12)

@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--num-coarse", type=int, default=64)
     ap.add_argument("--num-fine", type=int, default=64)
     ap.add_argument("--precision", default="fast")
+    ap.add_argument("--impl", default="fused", choices=["fused", "dropin"],
+                    help="fused: nerf/fused_train.py (libnfb launches only); dropin: run_one_iter_of_nerf + torch loss / Adam, as the unmodified script does")
     a = ap.parse_args()
     import nerface_oracle as O
     import nerf
@@ -68,8 +70,24 @@ def main():
     idx = [torch.randint(0, H * W, (a.rays,), device=dev, generator=g) for _ in range(n_steps)]
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_steps)]
     eng = nerf._engine.renderer_for(dev)
+    trainer = None
+    if a.impl == "fused":
+        from nerf import fused_train
+        trainer = fused_train.FusedTrainer(mc, mf, n_latent=16, lr=5e-4, num_coarse=a.num_coarse, num_fine=a.num_fine, perturb=True,
+                                           noise_std=0.1, near=0.2, far=0.8, latent_reg=0.005, precision=a.precision)
+
+    def step_fused(i):
+        sel = idx[i][rank * per_rank:(rank + 1) * per_rank]
+        ev[i][0].record()
+        loss = trainer.gradients(ro[sel], rd[sel], target_img[sel], expr, 3, background=bg[sel], world=world, n_total=a.rays,
+                                 events=(ev[i][1], ev[i][2]))
+        trainer.update()
+        ev[i][3].record()
+        return loss.sum()
 
     def step(i):
+        if trainer is not None:
+            return step_fused(i)
         sel = idx[i][rank * per_rank:(rank + 1) * per_rank]
         ev[i][0].record()
         out = nerf.run_one_iter_of_nerf(H, W, fr["intrinsics"], mc, mf, ro[sel], rd[sel], cfg, mode="train", expressions=expr,
@@ -121,7 +139,7 @@ def main():
             "metric": "training rays/sec (2048-ray batches, fwd + bwd + Adam)", "value": a.rays / (step_ms * 1e-3), "unit": "rays/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": step_ms,
             "ms_forward_and_loss": fwd, "ms_backward": bwd, "ms_optimizer": ost, "wall_ms_per_step": 1e3 * wall / a.steps,
-            "config": {"workload": f"{a.rays} rays/iter, {a.num_coarse}c+{a.num_fine}f, perturb + noise 0.1, Adam", "precision": a.precision,
+            "impl": a.impl, "config": {"workload": f"{a.rays} rays/iter, {a.num_coarse}c+{a.num_fine}f, perturb + noise 0.1, Adam", "precision": a.precision,
                        "parallelism": f"dp{world} (ray batch sharded, one flat gradient all-reduce)"},
             "gpu_launches_per_step": (eng.launch_count() - l0) / a.steps,
             "roofline": {"bound": "tensor", "achieved": flop / (step_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
