@@ -25,6 +25,36 @@ __device__ __forceinline__ float w6_elem(const NetParams& a, int n, int k) {
   for (int j = 0; j < 256; ++j) acc += (double)left[j] * (double)Wf[j * 256 + k];
   return (float)acc;
 }
+// Eight entries at once: one pass over j shares the operand both callers have in common.
+//   w6_row8: W6[n][k0 .. k0+8)  (forward stream: eight consecutive K of one output row)
+//   w6_col8: W6[n0 .. n0+8)[k]  (backward stream: eight consecutive output rows of one column)
+__device__ __forceinline__ void w6_row8(const NetParams& a, int n, int k0, float (&out)[8]) {
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (n <= 128) {
+    const float* left = (n < 128) ? (a.p[16] + (size_t)n * 280) : a.p[14];
+    const float* Wf = a.p[12] + k0;
+    for (int j = 0; j < 256; ++j) {
+      const double l = (double)left[j];
+      const float4 w0 = *reinterpret_cast<const float4*>(Wf + (size_t)j * 256), w1 = *reinterpret_cast<const float4*>(Wf + (size_t)j * 256 + 4);
+      acc[0] += l * (double)w0.x; acc[1] += l * (double)w0.y; acc[2] += l * (double)w0.z; acc[3] += l * (double)w0.w;
+      acc[4] += l * (double)w1.x; acc[5] += l * (double)w1.y; acc[6] += l * (double)w1.z; acc[7] += l * (double)w1.w;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) out[e] = (float)acc[e];
+}
+__device__ __forceinline__ void w6_col8(const NetParams& a, int n0, int k, float (&out)[8]) {
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const float* Wf = a.p[12] + k;
+  const float* left = a.p[16] + (size_t)n0 * 280;  // rows n0 .. n0+7 < 128 of layers_dir.0[:, :256]
+  for (int j = 0; j < 256; ++j) {
+    const double w = (double)Wf[(size_t)j * 256];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += (double)left[(size_t)e * 280 + j] * w;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) out[e] = (float)acc[e];
+}
 __device__ __forceinline__ float b6_elem(const NetParams& a, int n) {
   if (n > 128) return 0.f;
   const float* left = (n < 128) ? (a.p[16] + (size_t)n * 280) : a.p[14];
@@ -52,12 +82,14 @@ __device__ __forceinline__ void pack_fwd_chunk(const NetParams& a, int s, int u,
   const int n = (ui.h ? si.nh0 : 0) + n_local;  // row of the step's logical weight matrix
   __align__(16) __half hi[8];
   __align__(16) __half lo[8];
+  float w6v[8];
+  if (s == 6) w6_row8(a, n < n_valid ? n : 999, ui.ka * 64 + c16 * 8, w6v);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int k = ui.ka * 64 + c16 * 8 + e;  // logical K index of this step
     float w = 0.f;
     if (n < n_valid) {
-      if (s == 6) w = w6_elem(a, n, k);
+      if (s == 6) w = w6v[e];
       else if (si.pe_first) {
         if (k < kDimXyz) w = src[(size_t)n * ld + k];
         else if (k >= 64) w = src[(size_t)n * ld + (kDimXyz + kDimCond) + (k - 64)];
@@ -109,6 +141,8 @@ __device__ __forceinline__ void pack_bwd_chunk(const NetParams& a, int s, int u,
   const bool op_atom = si.pe_first && u == 0;
   const int hid = u - si.pe_first;  // TMEM atom index
   __align__(16) __half h[8];
+  float w6v[8];
+  if (s == 3 && !op_atom) w6_col8(a, hid * 64 + c16 * 8, n, w6v);  // M1^T: eight consecutive rows of M1 in column n
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int kl = c16 * 8 + e;        // k inside the atom
@@ -119,7 +153,7 @@ __device__ __forceinline__ void pack_bwd_chunk(const NetParams& a, int s, int u,
       case 1: w = a.p[20][kk * 128 + n]; break;                                    // layers_dir.2.weight[kk][n]
       case 2: w = a.p[18][kk * 128 + n]; break;                                    // layers_dir.1
       case 3: if (op_atom) { if (kl == 3) w = w6_elem(a, 128, n); }                // m2 = fc_alpha . fc_feat
-              else w = w6_elem(a, kk, n); break;                                   // M1 = layers_dir.0[:, :256] . fc_feat
+              else w = w6v[e]; break;                                              // M1 = layers_dir.0[:, :256] . fc_feat
       case 4: w = a.p[10][kk * 256 + n]; break;                                    // layers_xyz.5
       case 5: w = a.p[8][kk * 256 + n]; break;                                     // layers_xyz.4
       case 6: w = a.p[6][(size_t)kk * 427 + (kDimXyz + kDimCond) + n]; break;      // layers_xyz.3[:, 171:]

@@ -68,12 +68,14 @@ constexpr int kOffSort = kOffBins + 2 * kRowsC * 4;            // [kSortMax] pad
 static_assert(kSortMax >= 2 * kRowsF, "the fine pass's compositing weights live in the sort scratch");
 constexpr int kOffDirBias = kOffSort + kSortMax * 4;           // [3][4 rays][128]: coarse network (by unit parity: C(0), C(1) are
                                                                // consecutive jobs), fine network
-constexpr int kOffRay = kOffDirBias + 3 * 4 * 128 * 4;         // [4 units in flight][4 rays] RayP
-constexpr int kOffBars = kOffRay + 4 * 4 * kRayFloats * 4;
+constexpr int kOffRay = kOffDirBias + 3 * 4 * 128 * 4;         // [3 units in flight][4 rays] RayP: unit u is set up while u - 2 is
+                                                               // in its fine pass and u - 1 waits for its resampling
+constexpr int kOffStage = kOffRay + 3 * 4 * kRayFloats * 4;      // [24] outputs of one pass of one unit: rgb[4][3] disp[4] acc[4] w_last[4]
+constexpr int kOffBars = kOffStage + 24 * 4;
 constexpr int kNumBars = 2 * kNumSlots + 12;                   // full[] empty[] gate[2] accfull[2] pefree[2] peready[2] rawready[2] rawfree[2]
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
-static_assert(kOffBias % 16 == 0 && kOffRawC % 16 == 0 && kOffRawF % 16 == 0 && kOffBars % 8 == 0, "alignment");
+static_assert(kOffBias % 16 == 0 && kOffRawC % 16 == 0 && kOffRawF % 16 == 0 && kOffStage % 16 == 0 && kOffBars % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 struct JobIt {
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
       const bool live = prow < rows;
       const int r = live ? prow / S : 0;
       const int i = live ? prow - r * S : 0;
-      const RayP* rayp = rayp_all + (u & 3) * 4;
+      const RayP* rayp = rayp_all + (u % 3) * 4;
       const float* bias_n = reinterpret_cast<const float*>(smem + kOffBias) + pass * kBiasFloats;
       const float* dirbias = reinterpret_cast<const float*>(smem + kOffDirBias) + (pass ? 2 : (u & 1)) * 512;
       float4* raw = reinterpret_cast<float4*>(smem + (pass ? kOffRawF : kOffRawC));
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
 
     // ---- per-ray constants of unit iteration `it` (ray slot e = x * R + r) and the coarse network's direction term
     auto ray_setup = [&](int it) {
-      RayP* rayp = rayp_all + (it & 3) * 4;
+      RayP* rayp = rayp_all + (it % 3) * 4;
       const int unit = blockIdx.x + it * gridDim.x;
       if (stid < RR) {
         RayP& rp = rayp[stid];
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
     };
     // per-ray additive term of layers_dir.0 of network `pass`: W[:, 256:280] . PE_dir; thread = output feature
     auto dir_term = [&](int it, int pass) {
-      const RayP* rayp = rayp_all + (it & 3) * 4;
+      const RayP* rayp = rayp_all + (it % 3) * 4;
       const float* wt = p.wd0b_t[pass];
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
     };
     // stratified depths of the coarse pass (train_utils.py:56-76)
     auto z_coarse = [&](int it) {
-      const RayP* rayp = rayp_all + (it & 3) * 4;
+      const RayP* rayp = rayp_all + (it % 3) * 4;
       float* zc = zc_all + (it & 1) * (2 * kRowsC);
       for (int k = stid; k < RR * nc; k += kSamplerThreads) {
         const int e = k / nc, i = k - e * nc;
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
     };
     // positional encoding of tile t of `pass` of both streams into the PE buffers, each after its previous reader is done
     auto encode = [&](int it, int pass, int t) {
-      const RayP* rayp = rayp_all + (it & 3) * 4;
+      const RayP* rayp = rayp_all + (it % 3) * 4;
       const float* zc = zc_all + (it & 1) * (2 * kRowsC);
       const int S = pass ? SF : nc, rows = R * S;
 #pragma unroll
@@ -498,28 +500,49 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
       ph_pefree ^= 1;
     };
     // compositing of one pass of unit `it`: warp sw renders ray slot sw (and sw + 4 never exists: RR <= 4)
+    // Compositing of one pass of unit `it`: warp sw renders ray slot sw into the staging block; store_outputs() then writes the
+    // unit's results with 16-byte stores (the 2R rays of a unit are consecutive in every output array).
+    float* stage = reinterpret_cast<float*>(smem + kOffStage);
     auto composite_pass = [&](int it, int pass) {
-      const RayP* rayp = rayp_all + (it & 3) * 4;
+      const RayP* rayp = rayp_all + (it % 3) * 4;
       const float* zc = zc_all + (it & 1) * (2 * kRowsC);
       const int S = pass ? SF : nc;
       if (sw < RR && rayp[sw].valid) {
         const RayP& rp = rayp[sw];
-        const int g = rp.gidx;
         const int x = sw / R, rr = sw - x * R;
         const float4* raw = (pass ? raw_f + x * kRowsF : raw_c + x * kRowsC) + rr * S;
         const float* z = (pass ? zf + x * kRowsF : zc + x * kRowsC) + rr * S;
         float* wbuf = (pass ? scr_sort + x * kRowsF : scr_w + x * kRowsC) + rr * S;
-        float* o_rgb = pass ? p.rgb_f : p.rgb_c;
-        float* o_disp = pass ? p.disp_f : p.disp_c;
-        float* o_acc = pass ? p.acc_f : p.acc_c;
-        const float wl = composite_ray(raw, z, wbuf, S, rp.dnorm, p.white_bkgd != 0, o_rgb ? o_rgb + 3 * (size_t)g : nullptr,
-                                       o_disp ? o_disp + g : nullptr, o_acc ? o_acc + g : nullptr, lane);
-        if (pass == 1 && lane == 0 && p.w_last) p.w_last[g] = wl;
+        const float wl = composite_ray(raw, z, wbuf, S, rp.dnorm, p.white_bkgd != 0, stage + 3 * sw, stage + 12 + sw, stage + 16 + sw, lane);
+        if (lane == 0) stage[20 + sw] = wl;
+      }
+    };
+    // after a sampler barrier: the staged outputs of unit `it` -> global memory.  Full unit of 4 valid rays: float4 stores
+    // (rgb: 3 per unit at 48-byte stride, the scalars 1 each); otherwise (last unit, R = 1) per-ray scalar stores.
+    auto store_outputs = [&](int it, int pass) {
+      const RayP* rayp = rayp_all + (it % 3) * 4;
+      float* o_rgb = pass ? p.rgb_f : p.rgb_c;
+      float* o_disp = pass ? p.disp_f : p.disp_c;
+      float* o_acc = pass ? p.acc_f : p.acc_c;
+      float* o_wl = (pass == 1) ? p.w_last : nullptr;
+      const int g0 = rayp[0].gidx;
+      const bool vec = (RR == 4) && rayp[3].valid;
+      if (vec) {
+        if (stid < 3 && o_rgb) reinterpret_cast<float4*>(o_rgb + 3 * (size_t)g0)[stid] = reinterpret_cast<const float4*>(stage)[stid];
+        else if (stid == 3 && o_disp) *reinterpret_cast<float4*>(o_disp + g0) = reinterpret_cast<const float4*>(stage)[3];
+        else if (stid == 4 && o_acc) *reinterpret_cast<float4*>(o_acc + g0) = reinterpret_cast<const float4*>(stage)[4];
+        else if (stid == 5 && o_wl) *reinterpret_cast<float4*>(o_wl + g0) = reinterpret_cast<const float4*>(stage)[5];
+      } else if (stid < RR && rayp[stid].valid) {
+        const int g = rayp[stid].gidx;
+        if (o_rgb) { o_rgb[3 * (size_t)g] = stage[3 * stid]; o_rgb[3 * (size_t)g + 1] = stage[3 * stid + 1]; o_rgb[3 * (size_t)g + 2] = stage[3 * stid + 2]; }
+        if (o_disp) o_disp[g] = stage[12 + stid];
+        if (o_acc) o_acc[g] = stage[16 + stid];
+        if (o_wl) o_wl[g] = stage[20 + stid];
       }
     };
     // everything between the passes of unit `it`: composite the coarse pass, resample, sort -> zf
     auto between_passes = [&](int it) {
-      const RayP* rayp = rayp_all + (it & 3) * 4;
+      const RayP* rayp = rayp_all + (it % 3) * 4;
       const float* zc = zc_all + (it & 1) * (2 * kRowsC);
       mbar_wait(bar_rawready, ph_rawready0);  // C(it) complete
       ph_rawready0 ^= 1;
@@ -560,6 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
       }
       sbar();
       if (stid == 0) mbar_arrive(bar_rawfree);  // the coarse (colour, sigma) buffer may be overwritten by C(it + 1)
+      store_outputs(it, 0);
       // fine samples of every ray into scr_sort[e * P2 + j], padded with +inf
       for (int k = stid; k < RR * P2; k += kSamplerThreads) {
         const int e = k / P2, j = k - e * P2;
@@ -634,6 +658,8 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
       composite_pass(it, 1);
       sbar();
       if (stid == 0) mbar_arrive(bar_rawfree + 8);
+      store_outputs(it, 1);
+      sbar();  // the staging block is reused by the next pass's compositing
     };
 
     auto prepare = [&](int u, int pass, int t) {

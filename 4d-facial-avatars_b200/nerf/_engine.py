@@ -55,17 +55,24 @@ class Renderer:
         capi.check(capi.lib.nfb_create(C.byref(dims), idx, C.byref(h)), "create")
         self._h = h
         self._lin = {}
+        self._plist = {}
         self._versions = [None, None]
         self._keep = [None, None]  # contiguous FP32 copies handed to the pack kernels
         self.train_token = 0       # bumped by every training forward: the handle keeps ONE saved state
         weakref.finalize(self, capi.lib.nfb_destroy, h)
 
-    @staticmethod
-    def _fingerprint(model):
+    def _params(self, model):
+        """The model's 26 parameters in PARAM_ORDER; the walk over named_parameters() is cached per module object."""
+        cached = self._plist.get(id(model))
+        if cached is None or cached[0]() is not model:
+            sd = dict(model.named_parameters())
+            cached = self._plist[id(model)] = (weakref.ref(model), [sd[k] for k in PARAM_ORDER])
+        return cached[1]
+
+    def _fingerprint(self, model):
         """(identity, storage, in-place version) of every parameter.  Writes that bypass autograd's version counter
         (`p.data.copy_()`, external kernels) are invisible here: call invalidate() after them."""
-        sd = dict(model.named_parameters())
-        return (id(model),) + tuple((sd[k].data_ptr(), sd[k]._version) for k in PARAM_ORDER)
+        return (id(model),) + tuple((p.data_ptr(), p._version) for p in self._params(model))
 
     def invalidate(self):
         """Force a re-pack of both networks at the next render (after parameter writes torch cannot see)."""
@@ -84,8 +91,7 @@ class Renderer:
             fp = self._fingerprint(model)
             if fp == self._versions[which]:
                 continue
-            sd = dict(model.named_parameters())
-            tensors = [_f32c(sd[k], self.device) for k in PARAM_ORDER]
+            tensors = [_f32c(t, self.device) for t in self._params(model)]
             arr = (C.c_void_p * 26)(*[t.data_ptr() for t in tensors])
             capi.check(capi.lib.nfb_load_weights(self._h, which, arr, _stream()), "load_weights")
             self._keep[which] = tensors
