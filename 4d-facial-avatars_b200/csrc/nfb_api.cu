@@ -129,6 +129,8 @@ int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
     nfb::NetBuffers& nb = h->net[n];
     NFB_CUDA(dev_alloc(&nb.stream_x1, nfb::kStreamBytesX1));
     NFB_CUDA(dev_alloc(&nb.stream_x3, nfb::kStreamBytesX3));
+    NFB_CUDA(dev_alloc(&nb.w6, 144 * 256));
+    NFB_CUDA(dev_alloc(&nb.b6, 144));
     NFB_CUDA(dev_alloc(&nb.bias_static, nfb::kBiasFloats));
     NFB_CUDA(dev_alloc(&nb.bias_frame, nfb::kBiasFloats));
     NFB_CUDA(dev_alloc(&nb.w0c, 256 * nfb::kDimCond));
@@ -164,7 +166,7 @@ int nfb_destroy(NfbHandle* h) {
   cudaSetDevice(h->device);
   for (int n = 0; n < 2; ++n) {
     nfb::NetBuffers& nb = h->net[n];
-    cudaFree(nb.stream_x1); cudaFree(nb.stream_x3); cudaFree(nb.bias_static);
+    cudaFree(nb.stream_x1); cudaFree(nb.stream_x3); cudaFree(nb.w6); cudaFree(nb.b6); cudaFree(nb.bias_static);
     cudaFree(nb.bias_frame); cudaFree(nb.w0c); cudaFree(nb.w3c); cudaFree(nb.wd0b_t); cudaFree(nb.stream_bwd);
     cudaFree(h->tr.acc[n]);
   }
@@ -490,12 +492,8 @@ int nfb_render_backward(NfbHandle* h, const NfbOutGrads* og, const float* const 
       if (rc) return rc;
     }
   }
-  for (int net = 0; net < (fine ? 2 : 1); ++net)
-    NFB_CUDA(nfb::launch_finalize(net ? params_fine : params_coarse, net ? grads_fine : grads_coarse, tr.acc[net], tr.cond, st,
-                                  &h->launches));
-  if (grad_latent)
-    NFB_CUDA(nfb::launch_latent_grad(params_coarse, fine ? params_fine : nullptr, tr.acc[0], tr.acc[1], grad_latent, st,
-                                     &h->launches));
+  NFB_CUDA(nfb::launch_finalize_all(params_coarse, grads_coarse, tr.acc[0], fine ? params_fine : nullptr, fine ? grads_fine : nullptr,
+                                    tr.acc[1], tr.cond, grad_latent, st, &h->launches));
   return NFB_OK;
 }
 

@@ -12,6 +12,8 @@ namespace nfb {
 struct NetBuffers {
   uint8_t* stream_x1 = nullptr;  // kStreamBytesX1: FP16 weights, swizzled units in execution order
   uint8_t* stream_x3 = nullptr;  // kStreamBytesX3: hi unit, lo unit, ...
+  float* w6 = nullptr;           // [144,256] folded layers_dir.0 / fc_alpha
+  float* b6 = nullptr;           // [144]
   float* bias_static = nullptr;  // [kBiasFloats]
   float* bias_frame = nullptr;   // [kBiasFloats] bias_static + per-frame fold (what the kernel reads)
   float* w0c = nullptr;          // [256,108] conditioning columns of layers_xyz.0
@@ -92,12 +94,11 @@ cudaError_t train_kernels_setup();
 cudaError_t launch_composite_bwd(const CompBwdParams& q, float* scal, cudaStream_t st, long long* launches);
 cudaError_t launch_chain(const ChainParams& p, int num_sms, cudaStream_t st, long long* launches);
 cudaError_t launch_dw(const DwParams& p, int num_sms, cudaStream_t st, long long* launches);
-cudaError_t launch_finalize(const float* const params[26], float* const grads[26], const float* acc, const float* cond,
-                            cudaStream_t st, long long* launches);
-cudaError_t launch_latent_grad(const float* const params_c[26], const float* const params_f[26], const float* acc_c,
-                               const float* acc_f, float* out, cudaStream_t st, long long* launches);
+cudaError_t launch_finalize_all(const float* const params_c[26], float* const grads_c[26], const float* acc_c,
+                                const float* const params_f[26], float* const grads_f[26], const float* acc_f, const float* cond,
+                                float* latent_out, cudaStream_t st, long long* launches);
 
-// One launch: FP32 parameters of n_nets (1 or 2) networks -> forward / backward weight streams, bias block, conditioning and
+// Two launches (fold, pack): FP32 parameters of n_nets (1 or 2) networks -> forward / backward weight streams, bias block, conditioning and
 // direction columns (nfb_pack.cu: repack_kernel).
 cudaError_t launch_repack(NetBuffers* const nb[2], const float* const* const params[2], int n_nets, cudaStream_t st, long long* launches);
 // One launch: per-frame bias fold of the loaded networks + cond[108] = [expr / 3 ; latent].

@@ -2,7 +2,7 @@
 // train_transformed_rays.py:355-389 (mse(rgb_coarse) + mse(rgb_fine); the latent-code regulariser joins in the optimizer
 // kernel) as a gradient w.r.t. the rendered colours, and torch.optim.Adam (:391, YAML optimizer block) over ONE flat FP32
 // bucket holding both networks and the latent-code table, with optimizer.zero_grad() fused in.  The FP32 -> kernel-layout
-// re-pack that follows is repack_kernel (nfb_pack.cu), one more launch.
+// re-pack that follows is fold_feat_kernel + repack_kernel (nfb_pack.cu), two more launches.
 #include <cuda_runtime.h>
 
 #include "nfb_internal.h"

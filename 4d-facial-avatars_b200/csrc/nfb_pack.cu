@@ -1,6 +1,6 @@
 // nfb_pack.cu — load-time, per-optimizer-step and per-frame preparation kernels (not on the per-ray hot path):
-//   * repack_kernel    : ONE launch per weight update: fc_feat pre-multiplied into fc_alpha and layers_dir.0[:, :256] (FP64
-//                        accumulate, computed where needed), FP32 weights -> FP16 hi/lo as the swizzled shared-memory images the
+//   * fold_feat_kernel : fc_feat pre-multiplied into fc_alpha and layers_dir.0[:, :256] (FP64 accumulate), both networks
+//   * repack_kernel    : ONE launch per weight update, both networks: FP32 weights -> FP16 hi/lo as the swizzled shared-memory images the
 //                        render kernels bulk-copy (forward streams) and the transposed stream of the backward chain, static
 //                        biases, conditioning columns, transposed direction columns
 //   * frame_fold_kernel: per-frame expression/latent fold into the layer-0 / layer-3 biases
@@ -16,44 +16,17 @@ namespace nfb {
 // Folded step-6 matrix, computed where it is needed (FP64 accumulate, like a separate fold pass would):
 //   W6[n][k], n < 128: (Wd0[:, :256] @ Wf)[n][k];  n == 128: (wa @ Wf)[k];  n > 128: 0
 //   b6[n],    n < 128: bd0[n] + Wd0[n, :256] . bf;  n == 128: ba + wa . bf
-struct NetParams { const float* p[26]; };  // state_dict order (nfb.h: nfb_load_weights)
+struct NetParams { const float* p[26]; const float* w6; const float* b6; };  // state_dict order (nfb.h: nfb_load_weights) + the fold
 __device__ __forceinline__ float w6_elem(const NetParams& a, int n, int k) {
   if (n > 128) return 0.f;
   const float* left = (n < 128) ? (a.p[16] + (size_t)n * 280) : a.p[14];
   const float* Wf = a.p[12];
-  double acc = 0.0;
-  for (int j = 0; j < 256; ++j) acc += (double)left[j] * (double)Wf[j * 256 + k];
-  return (float)acc;
-}
-// Eight entries at once: one pass over j shares the operand both callers have in common.
-//   w6_row8: W6[n][k0 .. k0+8)  (forward stream: eight consecutive K of one output row)
-//   w6_col8: W6[n0 .. n0+8)[k]  (backward stream: eight consecutive output rows of one column)
-__device__ __forceinline__ void w6_row8(const NetParams& a, int n, int k0, float (&out)[8]) {
-  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (n <= 128) {
-    const float* left = (n < 128) ? (a.p[16] + (size_t)n * 280) : a.p[14];
-    const float* Wf = a.p[12] + k0;
-    for (int j = 0; j < 256; ++j) {
-      const double l = (double)left[j];
-      const float4 w0 = *reinterpret_cast<const float4*>(Wf + (size_t)j * 256), w1 = *reinterpret_cast<const float4*>(Wf + (size_t)j * 256 + 4);
-      acc[0] += l * (double)w0.x; acc[1] += l * (double)w0.y; acc[2] += l * (double)w0.z; acc[3] += l * (double)w0.w;
-      acc[4] += l * (double)w1.x; acc[5] += l * (double)w1.y; acc[6] += l * (double)w1.z; acc[7] += l * (double)w1.w;
-    }
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};  // four independent chains: the loop is bound by the FP64 add latency
+  for (int j = 0; j < 256; j += 4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] += (double)left[j + q] * (double)Wf[(j + q) * 256 + k];
   }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) out[e] = (float)acc[e];
-}
-__device__ __forceinline__ void w6_col8(const NetParams& a, int n0, int k, float (&out)[8]) {
-  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const float* Wf = a.p[12] + k;
-  const float* left = a.p[16] + (size_t)n0 * 280;  // rows n0 .. n0+7 < 128 of layers_dir.0[:, :256]
-  for (int j = 0; j < 256; ++j) {
-    const double w = (double)Wf[(size_t)j * 256];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += (double)left[(size_t)e * 280 + j] * w;
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) out[e] = (float)acc[e];
+  return (float)((acc[0] + acc[1]) + (acc[2] + acc[3]));
 }
 __device__ __forceinline__ float b6_elem(const NetParams& a, int n) {
   if (n > 128) return 0.f;
@@ -63,6 +36,16 @@ __device__ __forceinline__ float b6_elem(const NetParams& a, int n) {
   for (int j = 0; j < 256; ++j) b += (double)left[j] * (double)bf[j];
   return (float)b;
 }
+// Launch 1 of a re-pack: W6 [144][256] and b6 [144] of up to two networks (blockIdx.y); thread = (row n = blockIdx.x, column k):
+// the j loop reads left[j] as a warp broadcast and Wf[j][k] coalesced.
+struct FoldArgs { NetParams net[2]; float* w6[2]; float* b6[2]; };
+__global__ void __launch_bounds__(256) fold_feat_kernel(const FoldArgs f) {
+  const NetParams& a = f.net[blockIdx.y];
+  const int n = blockIdx.x, k = threadIdx.x;
+  f.w6[blockIdx.y][n * 256 + k] = w6_elem(a, n, k);
+  if (k == 0) f.b6[blockIdx.y][n] = b6_elem(a, n);
+}
+
 // step -> (source parameter index, leading dimension, valid output rows); step 6 is the folded matrix
 __device__ __forceinline__ int step_src(int s) { return s <= 5 ? 2 * s : (s == 7 ? 18 : (s == 8 ? 20 : 24)); }
 __device__ __forceinline__ int step_ld(int s) { return s == 0 ? 171 : (s == 3 ? 427 : (s <= 6 ? 256 : 128)); }
@@ -82,14 +65,12 @@ __device__ __forceinline__ void pack_fwd_chunk(const NetParams& a, int s, int u,
   const int n = (ui.h ? si.nh0 : 0) + n_local;  // row of the step's logical weight matrix
   __align__(16) __half hi[8];
   __align__(16) __half lo[8];
-  float w6v[8];
-  if (s == 6) w6_row8(a, n < n_valid ? n : 999, ui.ka * 64 + c16 * 8, w6v);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int k = ui.ka * 64 + c16 * 8 + e;  // logical K index of this step
     float w = 0.f;
     if (n < n_valid) {
-      if (s == 6) w = w6v[e];
+      if (s == 6) w = a.w6[n * 256 + k];
       else if (si.pe_first) {
         if (k < kDimXyz) w = src[(size_t)n * ld + k];
         else if (k >= 64) w = src[(size_t)n * ld + (kDimXyz + kDimCond) + (k - 64)];
@@ -114,7 +95,7 @@ __device__ __forceinline__ void gather_elem(const NetParams& g, int t, float* __
   if (t < kBiasFloats) {
     float v = 0.f;
     if (t < 1536) v = g.p[2 * (t / 256) + 1][t % 256];       // layers_xyz.{0..5}.bias
-    else if (t < 1680) v = b6_elem(g, t - 1536);              // folded layers_dir.0 / fc_alpha
+    else if (t < 1680) v = g.b6[t - 1536];                    // folded layers_dir.0 / fc_alpha
     else if (t < 1808) v = g.p[19][t - 1680];                 // layers_dir.1.bias
     else if (t < 1936) v = g.p[21][t - 1808];                 // layers_dir.2.bias
     else if (t < 1939) v = g.p[25][t - 1936];                 // fc_rgb.bias
@@ -141,8 +122,6 @@ __device__ __forceinline__ void pack_bwd_chunk(const NetParams& a, int s, int u,
   const bool op_atom = si.pe_first && u == 0;
   const int hid = u - si.pe_first;  // TMEM atom index
   __align__(16) __half h[8];
-  float w6v[8];
-  if (s == 3 && !op_atom) w6_col8(a, hid * 64 + c16 * 8, n, w6v);  // M1^T: eight consecutive rows of M1 in column n
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int kl = c16 * 8 + e;        // k inside the atom
@@ -152,8 +131,8 @@ __device__ __forceinline__ void pack_bwd_chunk(const NetParams& a, int s, int u,
       case 0: if (kl < 3) w = a.p[24][kl * 128 + n]; break;                       // fc_rgb.weight[kl][n]
       case 1: w = a.p[20][kk * 128 + n]; break;                                    // layers_dir.2.weight[kk][n]
       case 2: w = a.p[18][kk * 128 + n]; break;                                    // layers_dir.1
-      case 3: if (op_atom) { if (kl == 3) w = w6_elem(a, 128, n); }                // m2 = fc_alpha . fc_feat
-              else w = w6v[e]; break;                                              // M1 = layers_dir.0[:, :256] . fc_feat
+      case 3: if (op_atom) { if (kl == 3) w = a.w6[128 * 256 + n]; }               // m2 = fc_alpha . fc_feat
+              else w = a.w6[kk * 256 + n]; break;                                  // M1 = layers_dir.0[:, :256] . fc_feat
       case 4: w = a.p[10][kk * 256 + n]; break;                                    // layers_xyz.5
       case 5: w = a.p[8][kk * 256 + n]; break;                                     // layers_xyz.4
       case 6: w = a.p[6][(size_t)kk * 427 + (kDimXyz + kDimCond) + n]; break;      // layers_xyz.3[:, 171:]
@@ -166,8 +145,8 @@ __device__ __forceinline__ void pack_bwd_chunk(const NetParams& a, int s, int u,
   *reinterpret_cast<uint4*>(dst + off + n * 128 + ((c16 ^ (n & 7)) << 4)) = *reinterpret_cast<const uint4*>(h);
 }
 
-// ONE launch re-packs up to two networks: FP32 parameters -> forward streams (x1, hi/lo x3), transposed backward stream,
-// bias block, conditioning columns, direction columns.  Block ranges per network: [0, kFwdBlocks) forward chunks (8 blocks
+// Launch 2 re-packs up to two networks: FP32 parameters (+ the fold) -> forward streams (x1, hi/lo x3), transposed backward
+// stream, bias block, conditioning columns, direction columns.  Block ranges per network: [0, kFwdBlocks) forward chunks (8 blocks
 // per (step, unit)), then backward chunks, then the gather.  Used by nfb_load_weights and by the fused optimizer step.
 constexpr int kMaxFwdUnits = 5, kMaxBwdUnits = 4;
 constexpr int kFwdBlocks = 8 * kMaxFwdUnits * kNumSteps;   // 400
@@ -198,53 +177,68 @@ __global__ void __launch_bounds__(256) repack_kernel(const RepackArgs a) {
   gather_elem(np, b * 256 + threadIdx.x, a.bias_static[net], a.w0c[net], a.w3c[net], a.wd0b_t[net]);
 }
 
-// Per-frame conditioning in ONE launch.  Blocks 0..n_nets-1: bias_frame = bias_static, then rows of step 0 and step 3
-// += W[:, 63:171] . [expr/3 ; latent] of that network.  Last block: cond[108] = [expr/3 ; latent] (the backward's chain rule
-// through this fold needs it).
+// Per-frame conditioning in ONE launch.  Per network kFoldSlabs blocks: bias_frame = bias_static, then rows of step 0 and step 3
+// += W[:, 63:171] . [expr/3 ; latent] (coalesced row loads, the accumulation order of a scalar loop).  One more block:
+// cond[108] = [expr/3 ; latent] (the backward's chain rule through this fold needs it).
 struct FrameFoldArgs {
   const float *bias_static[2], *w0c[2], *w3c[2];
   float* bias_frame[2];
   float* cond;
   int n_nets;
 };
-__global__ void frame_fold_kernel(const float* __restrict__ expr, const float* __restrict__ latent, const FrameFoldArgs a) {
+constexpr int kFoldSlabs = 8;  // blocks per network: 64 of the 512 folded bias rows each (one warp per row, lanes over the 108 columns)
+__global__ void __launch_bounds__(256) frame_fold_kernel(const float* __restrict__ expr, const float* __restrict__ latent, const FrameFoldArgs a) {
   __shared__ float c[kDimCond];
   const int t = threadIdx.x;
   if (t < kDimExpr) c[t] = __fdiv_rn(expr[t], 3.0f);  // (expr * 1 / 3), models.py:241
   else if (t < kDimCond) c[t] = latent[t - kDimExpr];
   __syncthreads();
-  const int net = blockIdx.x;
+  const int net = blockIdx.x / kFoldSlabs, slab = blockIdx.x % kFoldSlabs;
   if (net >= a.n_nets) {
-    if (t < kDimCond) a.cond[t] = c[t];
+    if (slab == 0 && t < kDimCond) a.cond[t] = c[t];
     return;
   }
   const float* __restrict__ bias_static = a.bias_static[net];
-  const float* __restrict__ w0c = a.w0c[net];
-  const float* __restrict__ w3c = a.w3c[net];
   float* __restrict__ bias_frame = a.bias_frame[net];
-  for (int i = t; i < kBiasFloats; i += blockDim.x) {
-    float v = bias_static[i];
-    const float* w = nullptr;
-    int n = 0;
-    if (i < 256) { w = w0c; n = i; }
-    else if (i >= 768 && i < 1024) { w = w3c; n = i - 768; }
-    if (w) {
-      float acc = 0.f;
-      for (int j = 0; j < kDimCond; ++j) acc = fmaf(w[n * kDimCond + j], c[j], acc);
-      v += acc;
-    }
-    bias_frame[i] = v;
+  if (slab == 0)  // the entries no fold touches: steps 1, 2 and 4..9
+    for (int i = t; i < kBiasFloats; i += blockDim.x)
+      if (!(i < 256 || (i >= 768 && i < 1024))) bias_frame[i] = bias_static[i];
+  const int warp = t >> 5, lane = t & 31;
+  for (int r = warp; r < 64; r += 8) {
+    const int row = slab * 64 + r;                 // 0..255: layers_xyz.0, 256..511: layers_xyz.3
+    const int n = row & 255;
+    const float* __restrict__ w = (row < 256 ? a.w0c[net] : a.w3c[net]) + n * kDimCond;
+    // the same left-to-right fma chain a single thread would run (j ascending), split over lanes would change the rounding of
+    // the per-frame bias by ~1 ulp; keep the sequential order: lane 0 accumulates, the other lanes only prefetch into registers
+    float wv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wv[q] = (lane + 32 * q < kDimCond) ? w[lane + 32 * q] : 0.f;
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      for (int l = 0; l < 32; ++l) {
+        const float x = __shfl_sync(0xffffffffu, wv[q], l);
+        if (l + 32 * q < kDimCond) acc = fmaf(x, c[l + 32 * q], acc);
+      }
+    const int bi = (row < 256) ? n : 768 + n;
+    if (lane == 0) bias_frame[bi] = bias_static[bi] + acc;
   }
 }
 
 cudaError_t launch_repack(NetBuffers* const nb[2], const float* const* const params[2], int n_nets, cudaStream_t st,
                           long long* launches) {
   RepackArgs a;
+  FoldArgs f;
   for (int n = 0; n < n_nets; ++n) {
-    for (int i = 0; i < 26; ++i) a.net[n].p[i] = params[n][i];
+    for (int i = 0; i < 26; ++i) { a.net[n].p[i] = params[n][i]; f.net[n].p[i] = params[n][i]; }
+    f.net[n].w6 = f.net[n].b6 = nullptr;
+    f.w6[n] = nb[n]->w6; f.b6[n] = nb[n]->b6;
+    a.net[n].w6 = nb[n]->w6; a.net[n].b6 = nb[n]->b6;
     a.x1[n] = nb[n]->stream_x1; a.x3[n] = nb[n]->stream_x3; a.bwd[n] = nb[n]->stream_bwd;
     a.bias_static[n] = nb[n]->bias_static; a.w0c[n] = nb[n]->w0c; a.w3c[n] = nb[n]->w3c; a.wd0b_t[n] = nb[n]->wd0b_t;
   }
+  fold_feat_kernel<<<dim3(144, n_nets), 256, 0, st>>>(f);
+  ++*launches;
   repack_kernel<<<dim3(kRepackBlocks, n_nets), 256, 0, st>>>(a);
   ++*launches;
   return cudaGetLastError();
@@ -258,7 +252,7 @@ cudaError_t launch_frame_fold(NetBuffers* const nb[2], int n_nets, const float* 
   }
   a.cond = cond;
   a.n_nets = n_nets;
-  frame_fold_kernel<<<n_nets + 1, 256, 0, st>>>(expr, latent, a);
+  frame_fold_kernel<<<(n_nets + 1) * kFoldSlabs, 256, 0, st>>>(expr, latent, a);
   ++*launches;
   return cudaGetLastError();
 }

@@ -34,10 +34,14 @@ namespace nfb {
 // ================================================================================================
 // 1. compositing backward (SIMT; one thread per (pass, ray))
 // ================================================================================================
-__global__ void composite_bwd_kernel(const CompBwdParams q) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per (ray, pass); samples are lane-blocked (lane l owns samples [l*per, (l+1)*per)).  The forward product of
+// (1 - alpha + 1e-10) and the reverse affine recurrence  C_{i-1} = dLdw_i alpha_i + omega_i C_i  are both scans: in-lane
+// sequential, across lanes a shuffle scan (of products / of composed affine maps).
+__global__ void __launch_bounds__(256) composite_bwd_kernel(const CompBwdParams q) {
+  const int lane = threadIdx.x & 31;
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int npass = q.nf > 0 ? 2 : 1;
-  if (idx >= npass * q.n_rays) return;
+  if (idx >= npass * q.n_rays) return;  // whole warps
   const int pass = idx / q.n_rays;
   const int g = idx - pass * q.n_rays;
   const int S = pass ? q.s_fine : q.nc;
@@ -49,18 +53,51 @@ __global__ void composite_bwd_kernel(const CompBwdParams q) {
   const float gdisp = q.g_disp[pass] ? q.g_disp[pass][g] : 0.f;
   float g_acc = q.g_acc[pass] ? q.g_acc[pass][g] : 0.f;
   const float gwl = (pass == npass - 1 && q.g_wlast) ? q.g_wlast[g] : 0.f;
+  constexpr int kPer = 16;  // S <= 512
+  const int per = (S + 31) >> 5;
+  const int i0 = lane * per;
 
-  float Tarr[512];  // transmittance in front of each sample (local memory; S <= 512)
-  float T = 1.f, depth = 0.f, acc = 0.f;
-  for (int i = 0; i < S; ++i) {
-    const float delta = ((i < S - 1) ? (z[i + 1] - z[i]) : 1e10f) * dn;
-    const float sig = fmaxf(raw[i].w, 0.f) + (i == S - 1 ? 1e-6f : 0.f);
-    const float alpha = 1.f - expf(-sig * delta);
-    Tarr[i] = T;
-    const float w = alpha * T;
-    depth = fmaf(w, z[i], depth);
-    acc += w;
-    T *= (1.f - alpha) + 1e-10f;
+  // ---- forward: alpha, e = exp(-sigma delta) per sample; transmittance in front of this lane's block
+  float e_[kPer], zl[kPer];
+  float prod = 1.f;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = i0 + j;
+    e_[j] = 1.f; zl[j] = 0.f;
+    if (j < per && i < S) {
+      zl[j] = z[i];
+      const float delta = ((i < S - 1) ? (z[i + 1] - zl[j]) : 1e10f) * dn;
+      const float sig = fmaxf(raw[i].w, 0.f) + (i == S - 1 ? 1e-6f : 0.f);
+      e_[j] = expf(-sig * delta);
+      prod *= ((1.f - (1.f - e_[j])) + 1e-10f);
+    }
+  }
+  float incl = prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= t;
+  }
+  float T0 = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) T0 = 1.f;
+  float depth = 0.f, acc = 0.f;
+  {
+    float T = T0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      if (j < per && i0 + j < S) {
+        const float alpha = 1.f - e_[j];
+        const float w = alpha * T;
+        depth = fmaf(w, zl[j], depth);
+        acc += w;
+        T *= (1.f - alpha) + 1e-10f;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    depth += __shfl_xor_sync(0xffffffffu, depth, o);
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
   }
   // disp = 1 / max(1e-10, depth / acc)  (volume_rendering_utils.py:69); rgb += 1 - acc with a white background (:71-72)
   float g_depth = 0.f;
@@ -74,40 +111,85 @@ __global__ void composite_bwd_kernel(const CompBwdParams q) {
   }
   if (q.white_bkgd) g_acc -= (G0 + G1 + G2);
 
-  // Reverse sweep.  With omega_i = 1 - alpha_i + 1e-10 and C_i = sum_{k>i} dLdw_k alpha_k prod_{i<j<k} omega_j:
+  // ---- reverse sweep.  With omega_i = 1 - alpha_i + 1e-10 and C_i = sum_{k>i} dLdw_k alpha_k prod_{i<j<k} omega_j:
   //   dL/d alpha_i = T_i (dLdw_i - C_i),   C_{i-1} = dLdw_i alpha_i + omega_i C_i      (no division by omega).
+  // A lane's block maps the C entering at its top sample to the C leaving below its first: C_out = A + B C_in.
+  float A = 0.f, B = 1.f;
+#pragma unroll
+  for (int j = kPer - 1; j >= 0; --j) {
+    const int i = i0 + j;
+    if (j < per && i < S) {
+      const float4 r4 = raw[i];
+      const float dLdw = G0 * r4.x + G1 * r4.y + G2 * r4.z + g_acc + g_depth * zl[j] + (i == S - 1 ? gwl : 0.f);
+      const float om = e_[j] + 1e-10f;
+      A = fmaf(om, A, dLdw * (1.f - e_[j]));
+      B *= om;
+    }
+  }
+  // suffix composition over lanes 31 .. l+1 -> the C entering this lane (exclusive, from above)
+  float SA = A, SB = B;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float ta = __shfl_down_sync(0xffffffffu, SA, o), tb = __shfl_down_sync(0xffffffffu, SB, o);
+    if (lane + o < 32) { SA = fmaf(SB, ta, SA); SB *= tb; }  // this (lower) block applied AFTER the higher ones: A + B (ta + tb C)
+  }
+  float C = __shfl_down_sync(0xffffffffu, SA, 1);  // composed map of all higher lanes applied to C = 0
+  if (lane == 31) C = 0.f;
+
   const int unit = g / q.rays_per_unit, rr = g - unit * q.rays_per_unit;
   const int tile0 = unit * (q.tiles_c + q.tiles_f) + (pass ? q.tiles_c : 0);
-  float C = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, amax = 0.f;
-  for (int i = S - 1; i >= 0; --i) {
-    const float4 r4 = raw[i];
-    const float delta = ((i < S - 1) ? (z[i + 1] - z[i]) : 1e10f) * dn;
-    const float sig = fmaxf(r4.w, 0.f) + (i == S - 1 ? 1e-6f : 0.f);
-    const float e = expf(-sig * delta);
-    const float alpha = 1.f - e;
-    const float Ti = Tarr[i];
-    const float w = alpha * Ti;
-    const float dLdw = G0 * r4.x + G1 * r4.y + G2 * r4.z + g_acc + g_depth * z[i] + (i == S - 1 ? gwl : 0.f);
-    const float dalpha = Ti * (dLdw - C);
-    const float dsig = dalpha * (delta * e);  // d alpha / d sigma = delta exp(-sigma delta); (1e10 * 0) stays 0
-    float4 d;
-    d.w = (r4.w > 0.f) ? dsig : 0.f;          // ReLU (the +1e-6 on the last sample is an additive constant)
-    if (q.has_bg && i == S - 1) {
-      d.x = d.y = d.z = 0.f;                  // background colour is data (train_background=False)
-    } else {
-      d.x = w * G0 * r4.x * (1.f - r4.x);     // sigmoid
-      d.y = w * G1 * r4.y * (1.f - r4.y);
-      d.z = w * G2 * r4.z * (1.f - r4.z);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, amax = 0.f;
+  // transmittance in front of each sample of this block, walking down from the block's end
+  float Tj[kPer];
+  {
+    float T = T0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      Tj[j] = T;
+      if (j < per && i0 + j < S) T *= (1.f - (1.f - e_[j])) + 1e-10f;
     }
-    C = fmaf(e + 1e-10f, C, dLdw * alpha);
-    const int prow = rr * S + i;
-    reinterpret_cast<float4*>(q.draw)[(size_t)(tile0 + (prow >> 7)) * 128 + (prow & 127)] = d;
-    s0 += d.x; s1 += d.y; s2 += d.z; s3 += d.w;
-    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
   }
-  float* braw = q.acc[pass] + kAccBRaw;
-  atomicAdd(braw + 0, s0); atomicAdd(braw + 1, s1); atomicAdd(braw + 2, s2); atomicAdd(braw + 3, s3);
-  if (amax == amax && amax < 3.0e38f) atomicMax(q.absmax, __float_as_uint(amax));
+#pragma unroll
+  for (int j = kPer - 1; j >= 0; --j) {
+    const int i = i0 + j;
+    if (j < per && i < S) {
+      const float4 r4 = raw[i];
+      const float delta = ((i < S - 1) ? (z[i + 1] - zl[j]) : 1e10f) * dn;
+      const float e = e_[j];
+      const float alpha = 1.f - e;
+      const float Ti = Tj[j];
+      const float w = alpha * Ti;
+      const float dLdw = G0 * r4.x + G1 * r4.y + G2 * r4.z + g_acc + g_depth * zl[j] + (i == S - 1 ? gwl : 0.f);
+      const float dalpha = Ti * (dLdw - C);
+      const float dsig = dalpha * (delta * e);  // d alpha / d sigma = delta exp(-sigma delta); (1e10 * 0) stays 0
+      float4 d;
+      d.w = (r4.w > 0.f) ? dsig : 0.f;          // ReLU (the +1e-6 on the last sample is an additive constant)
+      if (q.has_bg && i == S - 1) {
+        d.x = d.y = d.z = 0.f;                  // background colour is data (train_background=False)
+      } else {
+        d.x = w * G0 * r4.x * (1.f - r4.x);     // sigmoid
+        d.y = w * G1 * r4.y * (1.f - r4.y);
+        d.z = w * G2 * r4.z * (1.f - r4.z);
+      }
+      C = fmaf(e + 1e-10f, C, dLdw * alpha);
+      const int prow = rr * S + i;
+      reinterpret_cast<float4*>(q.draw)[(size_t)(tile0 + (prow >> 7)) * 128 + (prow & 127)] = d;
+      s0 += d.x; s1 += d.y; s2 += d.z; s3 += d.w;
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    const float t = __shfl_xor_sync(0xffffffffu, amax, o);
+    amax = (t != t || amax != amax) ? __int_as_float(0x7fc00000) : fmaxf(amax, t);
+  }
+  if (lane == 0) {
+    float* braw = q.acc[pass] + kAccBRaw;
+    atomicAdd(braw + 0, s0); atomicAdd(braw + 1, s1); atomicAdd(braw + 2, s2); atomicAdd(braw + 3, s3);
+    if (amax == amax && amax < 3.0e38f) atomicMax(q.absmax, __float_as_uint(amax));
+  }
 }
 
 // scal[0] = loss scale (power of two bringing max |d raw| to about 2^10), scal[1] = 1 / scale.
@@ -653,9 +735,20 @@ __device__ __forceinline__ int fin_numel(int t) {
     default: return 0;  // layers_dir.3.*: unused by the forward (models.py:257) -> no gradient
   }
 }
-__global__ void finalize_kernel(const FinArgs a) {
-  const int t = blockIdx.y;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// ONE launch finishes both networks: blockIdx.y = network; blockIdx.x walks the 26 tensors back to back in 256-element blocks
+// (2.2 k blocks per network instead of a 427 x 26 grid that is mostly empty); the last block of network 0 computes d latent.
+struct FinAll { FinArgs net[2]; int nets; float* latent_out; };
+__device__ __forceinline__ int fin_blocks(int t) { return (fin_numel(t) + 255) >> 8; }
+__device__ void latent_grad_block(const FinAll& f);
+__global__ void __launch_bounds__(256) finalize_kernel(const FinAll f) {
+  const FinArgs& a = f.net[blockIdx.y];
+  int b = blockIdx.x, t = 0;
+  while (t < 26 && b >= fin_blocks(t)) { b -= fin_blocks(t); ++t; }
+  if (t == 26) {  // the block after the last tensor
+    if (blockIdx.y == 0 && b == 0 && f.latent_out) latent_grad_block(f);
+    return;
+  }
+  const int e = b * 256 + threadIdx.x;
   if (e >= fin_numel(t) || a.g[t] == nullptr) return;
   const float* acc = a.acc;
   const float* b6 = acc + acc_bias_off(6);
@@ -697,12 +790,7 @@ __global__ void finalize_kernel(const FinArgs a) {
       v = s;
       break;
     }
-    case 14: {  // fc_alpha.weight[0][j] = sum_k dm2[k] Wf[j][k] + dbs bf[j]
-      float s = dbs * a.p[13][e];
-      for (int k = 0; k < 256; ++k) s = fmaf(acc[kAccSig + k * 16 + 3], a.p[12][e * 256 + k], s);
-      v = s;
-      break;
-    }
+    case 14: return;  // fc_alpha.weight: 256 dot products of length 256 -> fin_dir0_kernel (one warp each, coalesced)
     case 15: v = dbs; break;
     case 16: {  // layers_dir.0.weight[i][j]: j < 256: sum_k dM1[i][k] Wf[j][k] + db6[i] bf[j]; else direction columns
       const int i = e / 280, j = e - i * 280;
@@ -723,9 +811,21 @@ __global__ void finalize_kernel(const FinArgs a) {
 }
 
 // layers_dir.0.weight[i][j], j < 256:  sum_k dM1[i][k] Wf[j][k] + db6[i] bf[j].  One warp per output element, lanes along k.
-__global__ void fin_dir0_kernel(const FinArgs a) {
+__global__ void fin_dir0_kernel(const FinAll f) {
+  const FinArgs& a = f.net[blockIdx.y];
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= 128 * 256) return;
+  if (w >= 128 * 256) {  // fc_alpha.weight[0][j] = sum_k dm2[k] Wf[j][k] + dbs bf[j]
+    const int j = w - 128 * 256;
+    if (j >= 256 || a.g[14] == nullptr) return;
+    const float* wf = a.p[12] + j * 256;
+    float s = 0.f;
+#pragma unroll
+    for (int k = lane; k < 256; k += 32) s = fmaf(a.acc[kAccSig + k * 16 + 3], wf[k], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) a.g[14][j] = s + a.acc[kAccBRaw + 3] * a.p[13][j];
+    return;
+  }
   const int i = w >> 8, j = w & 255;
   const float* dm1 = a.acc + kAcc6 + i * 256;
   const float* wf = a.p[12] + j * 256;
@@ -738,17 +838,18 @@ __global__ void fin_dir0_kernel(const FinArgs a) {
 }
 
 // d latent[j] = sum over networks, n of W0[n][139 + j] db0[n] + W3[n][139 + j] db3[n]
-struct LatArgs { const float* w0[2]; const float* w3[2]; const float* acc[2]; int nets; float* out; };
-__global__ void latent_grad_kernel(const LatArgs a) {  // one block of 256 threads: thread = (n-chunk of 32 rows, j)
+__device__ void latent_grad_block(const FinAll& f) {  // one block of 256 threads: thread = (n-chunk of 32 rows, j)
   __shared__ float part[8][kDimLatent];
   const int j = threadIdx.x & 31, c = threadIdx.x >> 5;
   float s = 0.f;
-  for (int net = 0; net < a.nets; ++net) {
-    const float* b0 = a.acc[net] + acc_bias_off(0);
-    const float* b3 = a.acc[net] + acc_bias_off(3);
+  for (int net = 0; net < f.nets; ++net) {
+    const float* b0 = f.net[net].acc + acc_bias_off(0);
+    const float* b3 = f.net[net].acc + acc_bias_off(3);
+    const float* w0 = f.net[net].p[0];
+    const float* w3 = f.net[net].p[6];
     for (int n = c * 32; n < c * 32 + 32; ++n) {
-      s = fmaf(a.w0[net][n * 171 + kDimXyz + kDimExpr + j], b0[n], s);
-      s = fmaf(a.w3[net][(size_t)n * 427 + kDimXyz + kDimExpr + j], b3[n], s);
+      s = fmaf(w0[n * 171 + kDimXyz + kDimExpr + j], b0[n], s);
+      s = fmaf(w3[(size_t)n * 427 + kDimXyz + kDimExpr + j], b3[n], s);
     }
   }
   part[c][j] = s;
@@ -756,7 +857,7 @@ __global__ void latent_grad_kernel(const LatArgs a) {  // one block of 256 threa
   if (c == 0) {
     float t = 0.f;
     for (int k = 0; k < 8; ++k) t += part[k][j];
-    a.out[j] = t;
+    f.latent_out[j] = t;
   }
 }
 
@@ -791,7 +892,7 @@ cudaError_t train_kernels_setup() {
 
 cudaError_t launch_composite_bwd(const CompBwdParams& q, float* scal, cudaStream_t st, long long* launches) {
   const int n = (q.nf > 0 ? 2 : 1) * q.n_rays;
-  composite_bwd_kernel<<<(n + 63) / 64, 64, 0, st>>>(q);
+  composite_bwd_kernel<<<(n + 7) / 8, 256, 0, st>>>(q);  // one warp per (ray, pass)
   ++*launches;
   scale_kernel<<<1, 1, 0, st>>>(q.absmax, scal);
   ++*launches;
@@ -831,27 +932,40 @@ cudaError_t launch_dw(const DwParams& p, int num_sms, cudaStream_t st, long long
   return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const float* const params[26], float* const grads[26], const float* acc, const float* cond,
-                            cudaStream_t st, long long* launches) {
-  FinArgs a;
-  for (int i = 0; i < 26; ++i) { a.p[i] = params[i]; a.g[i] = grads[i]; }
-  a.acc = acc;
-  a.cond = cond;
-  finalize_kernel<<<dim3((256 * 427 + 255) / 256, 26), 256, 0, st>>>(a);
-  ++*launches;
-  fin_dir0_kernel<<<128 * 256 * 32 / 256, 256, 0, st>>>(a);
-  ++*launches;
-  return cudaGetLastError();
+static int fin_numel_host(int t) {
+  switch (t) {
+    case 0: return 256 * 171;
+    case 6: return 256 * 427;
+    case 2: case 4: case 8: case 10: case 12: return 65536;
+    case 1: case 3: case 5: case 7: case 9: case 11: case 13: case 14: return 256;
+    case 15: return 1;
+    case 16: return 128 * 280;
+    case 18: case 20: return 128 * 128;
+    case 17: case 19: case 21: return 128;
+    case 24: return 3 * 128;
+    case 25: return 3;
+    default: return 0;
+  }
 }
 
-cudaError_t launch_latent_grad(const float* const params_c[26], const float* const params_f[26], const float* acc_c,
-                               const float* acc_f, float* out, cudaStream_t st, long long* launches) {
-  LatArgs a;
-  a.w0[0] = params_c[0]; a.w3[0] = params_c[6]; a.acc[0] = acc_c;
-  a.nets = params_f ? 2 : 1;
-  a.w0[1] = params_f ? params_f[0] : nullptr; a.w3[1] = params_f ? params_f[6] : nullptr; a.acc[1] = acc_f;
-  a.out = out;
-  latent_grad_kernel<<<1, 256, 0, st>>>(a);
+// Chain rule through the folds for one or both networks + d latent, two launches in all.
+cudaError_t launch_finalize_all(const float* const params_c[26], float* const grads_c[26], const float* acc_c,
+                                const float* const params_f[26], float* const grads_f[26], const float* acc_f, const float* cond,
+                                float* latent_out, cudaStream_t st, long long* launches) {
+  FinAll f;
+  f.nets = params_f ? 2 : 1;
+  f.latent_out = latent_out;
+  for (int i = 0; i < 26; ++i) {
+    f.net[0].p[i] = params_c[i]; f.net[0].g[i] = grads_c[i];
+    f.net[1].p[i] = params_f ? params_f[i] : nullptr; f.net[1].g[i] = params_f ? grads_f[i] : nullptr;
+  }
+  f.net[0].acc = acc_c; f.net[1].acc = acc_f;
+  f.net[0].cond = f.net[1].cond = cond;
+  int blocks = 1;  // + the latent block
+  for (int t = 0; t < 26; ++t) blocks += (fin_numel_host(t) + 255) / 256;
+  finalize_kernel<<<dim3(blocks, f.nets), 256, 0, st>>>(f);
+  ++*launches;
+  fin_dir0_kernel<<<dim3((128 * 256 + 256) * 32 / 256, f.nets), 256, 0, st>>>(f);
   ++*launches;
   return cudaGetLastError();
 }

@@ -4,7 +4,7 @@ as kernel launches of libnfb on ONE flat FP32 parameter bucket, with no torch.au
 gradient copies:
 
     set_frame (1 launch) -> training forward (1) -> loss gradient (1) -> backward (writes into the flat gradient bucket)
-    -> [one NCCL all-reduce of that bucket when the batch is sharded over ranks] -> Adam + zero_grad (1) -> re-pack (1)
+    -> [one NCCL all-reduce of that bucket when the batch is sharded over ranks] -> Adam + zero_grad (1) -> re-pack (2: fold, pack)
 
 The models keep their reference `state_dict` (their parameters become views of the bucket), so checkpoints, `.parameters()`
 and the drop-in `run_one_iter_of_nerf` keep working on the same objects.  torch is used for memory, the noise draws (in the

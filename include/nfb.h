@@ -217,7 +217,8 @@ typedef struct {
 int nfb_adam_step(NfbHandle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, const NfbAdam* hp,
                   void* stream);
 
-/* nfb_load_weights for both networks in ONE launch (params_fine may be NULL): the re-pack after an optimizer step. */
+/* nfb_load_weights for both networks at once (params_fine may be NULL), two launches (FP64 fold, pack): the re-pack after an
+ * optimizer step. */
 int nfb_repack(NfbHandle* h, const float* const params_coarse[26], const float* const params_fine[26], void* stream);
 
 /* ---- The steps either side of the path ----

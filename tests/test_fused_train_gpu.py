@@ -170,7 +170,8 @@ def test_adam_kernel_matches_torch_adam(env):
 
 
 def test_fused_step_launch_budget(env):
-    """After the backward: Adam (+ zero_grad) and the re-pack are ONE launch each; the whole step stays under 20 launches."""
+    """After the backward: Adam (+ zero_grad) is one launch and the re-pack two (FP64 fold, pack) — 3 in all; the whole step stays
+    under 20 launches."""
     nerf, _engine, fused_train, dev = env
     fr, ro, rd, bg, tgt, idx = _batches(dev, 3, 64)
     mc, mf = make_model(nerf, O.random_init_params(100), dev), make_model(nerf, O.random_init_params(101), dev)
@@ -184,7 +185,7 @@ def test_fused_step_launch_budget(env):
     l1 = eng.launch_count()
     eng.adam_step(tr.params, tr.grads, tr.exp_avg, tr.exp_avg_sq, 1e-4, 3)
     eng.repack(tr._pc, tr._pf)
-    assert eng.launch_count() - l1 == 2
+    assert eng.launch_count() - l1 == 3
     assert total <= 20, total
 
 
