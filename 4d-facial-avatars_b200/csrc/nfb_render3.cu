@@ -35,6 +35,7 @@
 #include "nfb_layout.h"
 #include "nfb_ptx.cuh"
 #include "nfb_render_common.cuh"
+#include "nfb_save.cuh"
 #include "nfb_tile2.cuh"
 
 namespace nfb {
@@ -102,7 +103,8 @@ template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setma
 // Positional encoding of sample row `row` (lane half `ch`) of tile t of one stream -> PE buffer (63 lanes + zero pad, FP16,
 // 128-byte swizzled).  z comes from the stream's depth buffer; rows beyond the pass encode depth 0 of ray 0 (never read back).
 __device__ __forceinline__ void encode_row(const RayP* __restrict__ rays_x /* the stream's R rays */, const float* __restrict__ z_x,
-                                           uint8_t* __restrict__ pe, int t, int S, int rows, int row, int ch) {
+                                           uint8_t* __restrict__ pe, int t, int S, int rows, int row, int ch,
+                                           uint8_t* __restrict__ rec /* training record of the tile, or null */) {
   const int prow = t * 128 + row;
   const bool live = prow < rows;
   const int r = live ? prow / S : 0;
@@ -138,16 +140,35 @@ __device__ __forceinline__ void encode_row(const RayP* __restrict__ rays_x /* th
     }
     f[31] = 0.f;
   }
+  uint32_t hh[16];
 #pragma unroll
   for (int qq = 0; qq < 4; ++qq) {
-    uint32_t hh[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) hh[e] = pack_f16x2(f[qq * 8 + 2 * e], f[qq * 8 + 2 * e + 1]);
+    for (int e = 0; e < 4; ++e) hh[qq * 4 + e] = pack_f16x2(f[qq * 8 + 2 * e], f[qq * 8 + 2 * e + 1]);
     const int off = row * 128 + (((ch * 4 + qq) ^ (row & 7)) << 4);
-    *reinterpret_cast<uint4*>(pe + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(pe + off) = make_uint4(hh[qq * 4], hh[qq * 4 + 1], hh[qq * 4 + 2], hh[qq * 4 + 3]);
+  }
+  if (rec) {  // training: the same 32 lanes as a transposed FP16 image for the weight gradients, and the row's ray's direction
+              // encoding (features [16 ch, 16 ch + 16) of 24) replicated per sample
+    store_t32(rec + kRecPE + img_row_base(64, row), row, 32 * ch, hh);
+    uint8_t* img = rec + kRecPEd + img_row_base(32, row);
+    const uint32_t cr = (uint32_t)((row & 63) >> 3);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ka = 16 * ch + 2 * e, kb = ka + 1;
+      const float a = (live && rp.valid && ka < kDimDir) ? rp.ped[ka] : 0.f;
+      const float b = (live && rp.valid && kb < kDimDir) ? rp.ped[kb] : 0.f;
+      const uint32_t w = pack_f16x2(a, b);
+      *reinterpret_cast<uint16_t*>(img + ka * 128 + ((cr ^ (uint32_t)(ka & 7)) << 4)) = (uint16_t)(w & 0xFFFFu);
+      *reinterpret_cast<uint16_t*>(img + kb * 128 + ((cr ^ (uint32_t)(kb & 7)) << 4)) = (uint16_t)(w >> 16);
+    }
   }
 }
 
+// SAVE = training forward: also writes the per-tile activation records (nfb_layout.h kRec*), per-sample (colour, ReLU input of
+// sigma), depths and |d| that nfb_render_backward reads — the same records as the one-tile kernel (unit 2U + x there = stream x
+// of unit U here).
+template <bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_constant__ RenderParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -196,6 +217,14 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
   const int first_in_cluster = (int)blockIdx.x - (int)cta_rank;
   const int n_iter = (p.n_units - first_in_cluster + (int)gridDim.x - 1) / (int)gridDim.x;  // units of work (2R rays) of this CTA
   const int Tc = p.tiles_c, Tf = p.tiles_f;
+  // training record of tile t of `pass` of stream x of unit iteration `it` (null outside SAVE mode / beyond the last real ray)
+  auto tile_rec = [&](int it, int pass, int x, int t) -> uint8_t* {
+    if constexpr (SAVE) {
+      const int u4 = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + x;  // unit index in the one-tile kernel's numbering
+      if (u4 * p.rays_per_unit < p.n_rays) return p.save_rec + ((size_t)u4 * (Tc + Tf) + (pass ? Tc : 0) + t) * kRecBytes;
+    }
+    return nullptr;
+  };
 
   // The job sequence every role walks (JobIt):  block b = -1: C(0);  block b >= 0: C(b+1) (if it exists), then F(b, 0..Tf-1).
   // A job is (u = the unit's iteration index, pass 0/1, t = tile pair of the pass).
@@ -273,6 +302,8 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
       mbar_wait(bar_peready + 8, ph_per);
       ph_per ^= 1;
 
+      uint8_t* rec0 = tile_rec(u, pass, 0, t);
+      uint8_t* rec1 = tile_rec(u, pass, 1, t);
       uint32_t keep0[32], keep1[32];  // half-0 results of streams X / Y, held until P is dead
       float sigma_raw0 = 0.f, sigma_raw1 = 0.f;
       for (int s = 0; s < kNumSteps; ++s) {
@@ -293,23 +324,28 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
             uint32_t (&keep)[32] = x ? keep1 : keep0;
             uint32_t hh[32];
             bool arrived = false;
+            int save_k0 = -1;         // SAVE: first feature of the 64 this event produced, -1: nothing to record
+            bool save_keep = false;   // SAVE: the 64 features are in `keep` (half 0) instead of `hh`
             float& sigma_raw = x ? sigma_raw1 : sigma_raw0;
             const RayP& rp = rayp[x * R + r];
             if (s <= 5) {
               if (h == 0) {  // outputs [64 ch, +64) of features 0..127 -> registers (gate signalled inside)
                 epi_load64_early(t_q + c0, smem_u32(bias_n + si.bias_off + c0), 0u, keep, bar_gate + x * 8, lane);
                 arrived = true;
+                save_k0 = c0; save_keep = true;
               } else {       // P_x is dead: store half 0 (K atom ch), convert half 1 (K atom 2 + ch)
                 store32(t_p + 32 * ch, keep);
                 epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + 128 + c0), 0u, hh);
                 store32(t_p + 64 + 32 * ch, hh);
                 tmem_wait_st();
+                save_k0 = 128 + c0;
               }
             } else if (s == 6) {
               if (h == 0) {
                 epi_load64_early(t_q + c0, smem_u32(bias_n + si.bias_off + c0), smem_u32(dirbias + (x * R + r) * 128 + c0), keep,
                                  bar_gate + x * 8, lane);
                 arrived = true;
+                save_k0 = c0; save_keep = true;
               } else {  // sigma = column 0 of the 16-wide second half; then g0 becomes the operand (K = 128)
                 if (ch == 0) {
                   uint32_t v[4];
@@ -324,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
               epi_load64(t_q + c0, smem_u32(bias_n + si.bias_off + c0), 0u, hh);
               store32(t_p + 32 * ch, hh);
               tmem_wait_st();
+              save_k0 = c0;
             } else if (ch == 0) {
               // fc_rgb output: colour and sigma per sample for compositing (volume_rendering_utils.py:29-33, 41-53)
               uint32_t v[4];
@@ -335,6 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
                 float sig = sigma_raw;
                 if (p.noise_std > 0.f && rp.valid)
                   sig = __fadd_rn(sig, __fmul_rn((pass ? p.noise_f : p.noise_c)[(size_t)rp.gidx * S + i], p.noise_std));
+                const float sig_in = sig;  // what the ReLU sees (volume_rendering_utils.py:52)
                 sig = fmaxf(sig, 0.f);
                 float4 pre;
                 if (i == S - 1) {
@@ -348,12 +386,28 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
                 }
                 pre.w = sig;
                 raw[x * raw_stride + prow] = pre;
+                if constexpr (SAVE) {  // what the compositing backward needs: colour (or bg) and the ReLU input
+                  if (rp.valid) reinterpret_cast<float4*>(pass ? p.save_raw_f : p.save_raw_c)[(size_t)rp.gidx * S + i] = make_float4(pre.x, pre.y, pre.z, sig_in);
+                }
               }
             }
             if (s < kNumSteps - 1 && !arrived) {  // Q_x has been read (and, after a step's last half, P_x holds the next operand)
               tc_fence_before_sync();
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_gate + x * 8);
+            }
+            if constexpr (SAVE) {  // after the gate: activation image + ReLU mask of the 64 features this event produced
+              uint8_t* rec = x ? rec1 : rec0;
+              if (rec && save_k0 >= 0) {
+                uint32_t a[16], b[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { a[j] = save_keep ? keep[j] : hh[j]; b[j] = save_keep ? keep[16 + j] : hh[16 + j]; }
+                uint8_t* img = rec + rec_x_off(s) + img_row_base(rec_width(s), row);
+                store_t32(img, row, save_k0, a);
+                store_t32(img, row, save_k0 + 32, b);
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(rec + kRecMask) + (s * 128 + row) * 8 + (save_k0 >> 5)) =
+                    make_uint2(relu_mask32(a), relu_mask32(b));
+              }
             }
           }
         }
@@ -418,6 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
           rp.dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
           if (has_bg) { rp.bg[0] = p.bg[3 * g]; rp.bg[1] = p.bg[3 * g + 1]; rp.bg[2] = p.bg[3 * g + 2]; }
           rp.dz = p.dir_z ? p.dir_z[g] : d2;
+          if constexpr (SAVE) p.save_dnorm[g] = rp.dnorm;
         } else {
           for (int k = 0; k < 3; ++k) { rp.o[k] = 0.f; rp.d[k] = 0.f; rp.bg[k] = 0.f; }
           rp.dnorm = 0.f;
@@ -477,6 +532,9 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
           z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
         }
         zc[x * kRowsC + rr * nc + i] = z;
+        if constexpr (SAVE) {
+          if (rp.valid) p.dbg_z_c[(size_t)rp.gidx * nc + i] = z;  // depths of the coarse pass for the compositing backward
+        }
       }
     };
     // positional encoding of tile t of `pass` of both streams into the PE buffers, each after its previous reader is done
@@ -491,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
         uint8_t* pe = smem + kOffPe + x * (kTileM * 128);
         for (int k = 0; k < 2; ++k) {  // 128 rows x 2 lane halves = 256 thread-tasks for 128 threads
           const int idx = k * kSamplerThreads + stid;
-          encode_row(rayp + x * R, z_x, pe, t, S, rows, idx & 127, idx >> 7);
+          encode_row(rayp + x * R, z_x, pe, t, S, rows, idx & 127, idx >> 7, tile_rec(it, pass, x, t));
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
@@ -651,6 +709,12 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
         zf[x * kRowsF + rr * SF + rank] = v;
       }
       sbar();
+      if constexpr (SAVE) {  // sorted depths of the fine pass for the compositing backward
+        for (int k = stid; k < RR * SF; k += kSamplerThreads) {
+          const int e = k / SF, i = k - e * SF;
+          if (rayp[e].valid) p.dbg_z_f[(size_t)rayp[e].gidx * SF + i] = zf[(e / R) * kRowsF + (e - (e / R) * R) * SF + i];
+        }
+      }
     };
     auto finish_fine = [&](int it) {  // F(it) complete -> composite it, then its buffers are free
       mbar_wait(bar_rawready + 8, ph_rawready1);
@@ -693,7 +757,9 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
 }  // namespace v7
 
 cudaError_t render3_kernel_setup() {
-  return cudaFuncSetAttribute(v7::render3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(v7::render3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(v7::render3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::kSmemBytes);
 }
 
 // Configurations the pipelined kernel's fixed shared-memory budget covers (nfb_api.cu falls back to nfb_render2.cu otherwise).
@@ -702,8 +768,9 @@ bool render3_supports(const RenderParams& p) {
   const int R = p.rays_per_unit;
   int p2 = 1;
   while (p2 < p.nf) p2 <<= 1;
-  return R * p.nc <= v7::kRowsC && R * p.s_fine <= v7::kRowsF && 2 * R * p2 <= v7::kSortMax && !p.save_rec && !p.dbg_act && !p.dbg_z_c &&
-         !p.dbg_raw_c && !p.dbg_z_f && !p.dbg_raw_f && !p.prof;
+  const bool fits = R * p.nc <= v7::kRowsC && R * p.s_fine <= v7::kRowsF && 2 * R * p2 <= v7::kSortMax && !p.dbg_act && !p.prof;
+  if (p.save_rec) return fits && !p.dbg_raw_c && !p.dbg_raw_f;  // training forward: depths go to dbg_z_c / dbg_z_f, the rest is in the records
+  return fits && !p.dbg_z_c && !p.dbg_raw_c && !p.dbg_z_f && !p.dbg_raw_f;
 }
 
 // `p` is prepared for the one-tile kernel (n_units = units of R rays); here a unit of work is 2R rays.
@@ -726,7 +793,7 @@ cudaError_t launch_render3(const RenderParams& p_in, int num_sms, cudaStream_t s
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, v7::render3_kernel, p);
+  cudaError_t e = p.save_rec ? cudaLaunchKernelEx(&cfg, v7::render3_kernel<true>, p) : cudaLaunchKernelEx(&cfg, v7::render3_kernel<false>, p);
   ++*launches;
   return e != cudaSuccess ? e : cudaGetLastError();
 }

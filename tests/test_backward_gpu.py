@@ -264,9 +264,11 @@ def test_parameter_gradients(ctx):
     assert e < 1e-2
 
 
-def test_training_forward_two_tile_matches_one_tile(built_lib, monkeypatch):
-    """Fast mode: the two-tile kernel also has a training (SAVE) variant (NFB_TRAIN_KERNEL=v6; not the default, it is slower
-    there); the one-tile kernel's SAVE variant is the reference here.  Both accumulate every output element over the same K sequence, so
+@pytest.mark.parametrize("kernel", ["v6", "v7"])
+def test_training_forward_two_tile_matches_one_tile(built_lib, monkeypatch, kernel):
+    """Fast mode: the two-tile kernel (NFB_TRAIN_KERNEL=v6) and the pipelined kernel (v7, the default training forward where its
+    shared-memory budget covers the sample counts) also have training (SAVE) variants; the one-tile kernel's SAVE variant
+    (NFB_TRAIN_KERNEL=v4) is the reference here.  Both accumulate every output element over the same K sequence, so
     outputs and the saved state (activation images, masks, encodings, colours, depths) must agree bit for bit, and the
     gradients computed from them to summation order (atomics)."""
     import nerf
@@ -307,10 +309,10 @@ def test_training_forward_two_tile_matches_one_tile(built_lib, monkeypatch):
         torch.cuda.synchronize()
         return out, rec, state, grads
 
-    monkeypatch.setenv("NFB_TRAIN_KERNEL", "v6")
-    out2, rec2, st2, g2 = run(_engine.Renderer(dev))                 # two-tile training forward (opt-in)
+    monkeypatch.setenv("NFB_TRAIN_KERNEL", kernel)
+    out2, rec2, st2, g2 = run(_engine.Renderer(dev))                 # two-tile / pipelined training forward
     monkeypatch.setenv("NFB_TRAIN_KERNEL", "v4")
-    out1, rec1, st1, g1 = run(_engine.Renderer(dev))                 # one-tile training forward (the default)
+    out1, rec1, st1, g1 = run(_engine.Renderer(dev))                 # one-tile training forward
     for k in ("rgb_coarse", "disp_coarse", "acc_coarse", "rgb_fine", "disp_fine", "acc_fine", "w_last"):
         assert torch.equal(out1[k], out2[k]), k
     for k in st1:
