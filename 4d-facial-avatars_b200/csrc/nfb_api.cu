@@ -113,18 +113,7 @@ int nfb_host_linspace(float* out, int n) {
   return NFB_OK;
 }
 
-int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
-  if (!dims || !out) return NFB_ERR_INVALID;
-  if (dims->num_encoding_fn_xyz != 10 || dims->num_encoding_fn_dir != 4 || dims->include_input_xyz != 1 ||
-      dims->include_input_dir != 0 || dims->dim_expression != nfb::kDimExpr || dims->dim_latent != nfb::kDimLatent)
-    return NFB_ERR_UNSUPPORTED;
-  NFB_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  NFB_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) return NFB_ERR_ARCH;
-  NfbHandle* h = new (std::nothrow) NfbHandle();
-  if (!h) return NFB_ERR_INVALID;
-  h->device = device;
+static int create_impl(NfbHandle* h, const cudaDeviceProp& prop) {
   h->num_sms = prop.multiProcessorCount;
   for (int n = 0; n < 2; ++n) {
     nfb::NetBuffers& nb = h->net[n];
@@ -161,6 +150,27 @@ int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
     // there (2048 rays, 64c+64f: v4 0.77 ms, v6 1.46 ms, v7 1.26 ms): the record is written as 16-bit transposed stores, 2304 per
     // row thread and tile, and with two streams the same eight row warps issue twice as many per unit of time.
     h->train_render3 = h->use_render3 && tk && std::strcmp(tk, "v7") == 0;
+  }
+  return NFB_OK;
+}
+
+
+int nfb_create(const NfbModelDims* dims, int device, NfbHandle** out) {
+  if (!dims || !out) return NFB_ERR_INVALID;
+  if (dims->num_encoding_fn_xyz != 10 || dims->num_encoding_fn_dir != 4 || dims->include_input_xyz != 1 ||
+      dims->include_input_dir != 0 || dims->dim_expression != nfb::kDimExpr || dims->dim_latent != nfb::kDimLatent)
+    return NFB_ERR_UNSUPPORTED;
+  NFB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  NFB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return NFB_ERR_ARCH;
+  NfbHandle* h = new (std::nothrow) NfbHandle();
+  if (!h) return NFB_ERR_INVALID;
+  h->device = device;
+  const int rc = create_impl(h, prop);
+  if (rc != NFB_OK) {  // free whatever was allocated before the failure
+    nfb_destroy(h);
+    return rc;
   }
   *out = h;
   return NFB_OK;
