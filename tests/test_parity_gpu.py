@@ -191,3 +191,25 @@ def test_stochastic_evaluation_like_the_shipped_yaml(env):
     with torch.no_grad():
         again = nerf.run_one_iter_of_nerf(H, W, fr["intrinsics"], mc, mf, ro, rd, cfg, mode="validation", **kw)
     assert float((again[3] - got[3]).abs().max()) > 0  # a second call draws fresh samples
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 9])
+def test_tiny_ray_counts_through_the_pipelined_kernel(env, n):
+    """Fewer rays than one unit of work / than one cluster of CTAs: partly valid units, idle CTAs, a single pipeline block."""
+    nerf, _engine, dev = env
+    fr = O.synthetic_frame(17, 4, 4)
+    ro, rd = O.ray_bundle(4, 4, fr["intrinsics"], fr["pose"])
+    ro, rd = ro.reshape(-1, 3)[:n].contiguous(), rd.reshape(-1, 3)[:n].contiguous()
+    bg = fr["bg"].reshape(-1, 3)[:n].contiguous()
+    pc, pf = O.random_init_params(100, True), O.random_init_params(101, True)
+    eng = _engine.renderer_for(dev)
+    eng.sync_weights(make_model(nerf, pc, dev), make_model(nerf, pf, dev))
+    eng.set_frame(fr["expr"].to(dev), fr["latent"].to(dev))
+    rays = torch.cat((ro, rd, torch.full((n, 1), 0.2), torch.full((n, 1), 0.8)), dim=-1)
+    with torch.no_grad():
+        ref = O.render_chunk(rays, pc, pf, O.Sampling(64, 128), fr["expr"], fr["latent"], bg, O.Noise())
+    out = eng.render(ro.to(dev), rd.to(dev), 0.2, 0.8, 64, 128, background=bg.to(dev), precision="fast")
+    torch.cuda.synchronize()
+    for name, r in zip(NAMES, ref):
+        tol = 4e-2 if name.startswith("disp") else 4e-3  # opaque-stress weights, fast mode (see test_render_gpu.tolerance)
+        assert float((out[name].cpu() - r).abs().max()) <= tol, (n, name)
