@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
 def test_sharded_paths_match_single_gpu(built_lib):
-    n = min(torch.cuda.device_count(), 8)
-    n = 1 << (n.bit_length() - 1)  # 2, 4 or 8 ranks: the 128-row test frame and the 256-ray batch split evenly
+    n = min(torch.cuda.device_count(), 4)
+    n = 1 << (n.bit_length() - 1)  # 2 or 4 ranks (verified on the box; bench.py covers 8): the 128-row test frame and the 256-ray batch split evenly
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
