@@ -109,7 +109,8 @@ def main():
         for gview_a, gview_b in zip(ta._gviews, tb._gviews):
             m = float(gview_a.abs().max())
             assert float((gview_a - gview_b).abs().max()) <= 1e-2 * max(m, 1e-12), (float((gview_a - gview_b).abs().max()), m)
-        tb.grads.copy_(ta.grads)  # keep the two trainers on one trajectory: this check is about the collective, not about Adam
+        ta.grads.copy_(tb.grads)  # keep the two trainers on one trajectory (the all-reduced bucket is identical on every rank;
+                                  # ta's own gradients carry per-rank atomics noise): this check is about the collective, not about Adam
         ta.update()
         tb.update()
         assert torch.equal(ta.params, tb.params)
