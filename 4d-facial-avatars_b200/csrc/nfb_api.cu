@@ -243,6 +243,14 @@ int nfb_adam_step(NfbHandle* h, float* params, float* grads, float* exp_avg, flo
   return NFB_OK;
 }
 
+int nfb_adam_step_dev(NfbHandle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, NfbAdamDev* dev_state,
+                      void* stream) {
+  if (!h || !params || !grads || !exp_avg || !exp_avg_sq || !dev_state || n <= 0) return NFB_ERR_INVALID;
+  NFB_CUDA(cudaSetDevice(h->device));
+  NFB_CUDA(nfb::launch_adam_dev(params, grads, exp_avg, exp_avg_sq, n, dev_state, static_cast<cudaStream_t>(stream), &h->launches));
+  return NFB_OK;
+}
+
 int nfb_set_frame(NfbHandle* h, const float* expression, const float* latent, void* stream) {
   if (!h || !expression || !latent) return NFB_ERR_INVALID;
   if (!h->net[0].loaded) return NFB_ERR_STATE;

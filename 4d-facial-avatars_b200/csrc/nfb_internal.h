@@ -107,6 +107,7 @@ cudaError_t launch_frame_fold(NetBuffers* const nb[2], int n_nets, const float* 
 // Training-step tail (nfb_optim.cu): d mse / d rgb (+ loss sums), Adam over a flat bucket with zero_grad fused.
 cudaError_t launch_loss_grad(const float* rgb_c, const float* rgb_f, const float* target, int n_rays, long long n_total, float* g_c,
                              float* g_f, float* loss, cudaStream_t st, long long* launches);
+cudaError_t launch_adam_dev(float* p, float* g, float* m, float* v, long long n, void* dev_state, cudaStream_t st, long long* launches);
 cudaError_t launch_adam(float* p, float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
                         float grad_scale, long long reg_off, float reg_w, cudaStream_t st, long long* launches);
 // precision: 0 = fast (x1), 1 = exact (x3).  num_sms = CTAs to launch at most.

@@ -84,6 +84,66 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   }
 }
 
+// Graph-capturable variant: the step counter, the learning-rate schedule and the regularised row live in DEVICE memory, so one
+// captured CUDA graph replays every iteration.  adam_prepare_kernel (1 thread) advances the step and derives this step's
+// scalars exactly as launch_adam does on the host (double precision); adam_dev_kernel is adam_kernel reading them.
+struct AdamDevState {  // mirrors NfbAdamDev (include/nfb.h)
+  int step, pad;
+  float lr0, decay_factor, decay_steps, b1, b2, eps, grad_scale, reg_w;
+  long long table_off;       // float offset of the latent table in the bucket (< 0: no regulariser)
+  const long long* row;      // device pointer to the current row index
+  float lr_over_bc1, sqrt_bc2;
+  long long reg_off;
+};
+__global__ void adam_prepare_kernel(AdamDevState* st) {
+  const int step = ++st->step;  // 1-based number of the step being taken
+  const int i = step - 1;       // the reference's loop index (train_transformed_rays.py:393-399: lr set AFTER step i)
+  const double lr = (i <= 0) ? (double)st->lr0 : (double)st->lr0 * pow((double)st->decay_factor, (double)(i - 1) / (double)st->decay_steps);
+  const double bc1 = 1.0 - pow((double)st->b1, (double)step), bc2 = 1.0 - pow((double)st->b2, (double)step);
+  st->lr_over_bc1 = (float)(lr / bc1);
+  st->sqrt_bc2 = (float)sqrt(bc2);
+  st->reg_off = (st->table_off >= 0 && st->row) ? st->table_off + (long long)kDimLatent * st->row[0] : -1;
+}
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ P, float* __restrict__ G, float* __restrict__ M, float* __restrict__ V,
+                                                       long long n, const AdamDevState* __restrict__ st) {
+  __shared__ float reg_inv_norm;
+  const long long reg_off = st->reg_off;
+  const float lr_over_bc1 = st->lr_over_bc1, sqrt_bc2 = st->sqrt_bc2, b1 = st->b1, b2 = st->b2, eps = st->eps, gs = st->grad_scale, reg_w = st->reg_w;
+  if (reg_off >= 0) {
+    if (threadIdx.x < 32) {
+      const float l = P[reg_off + threadIdx.x];
+      float s = l * l;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (threadIdx.x == 0) reg_inv_norm = s > 0.f ? rsqrtf(s) : 0.f;
+    }
+    __syncthreads();
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = G[i] * gs;
+    const float p = P[i];
+    if (reg_off >= 0 && i >= reg_off && i < reg_off + kDimLatent) g = fmaf(reg_w * reg_inv_norm, p, g);
+    float m = M[i], v = V[i];
+    m = fmaf(g - m, 1.f - b1, m);
+    v = fmaf(g * g, 1.f - b2, v * b2);
+    const float denom = sqrtf(v) / sqrt_bc2 + eps;
+    P[i] = p - lr_over_bc1 * (m / denom);
+    M[i] = m;
+    V[i] = v;
+    G[i] = 0.f;
+  }
+}
+cudaError_t launch_adam_dev(float* p, float* g, float* m, float* v, long long n, void* dev_state, cudaStream_t st, long long* launches) {
+  AdamDevState* s = static_cast<AdamDevState*>(dev_state);
+  adam_prepare_kernel<<<1, 1, 0, st>>>(s);
+  ++*launches;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_dev_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, s);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_loss_grad(const float* rgb_c, const float* rgb_f, const float* target, int n_rays, long long n_total, float* g_c,
                              float* g_f, float* loss, cudaStream_t st, long long* launches) {
   const int n = 3 * n_rays;

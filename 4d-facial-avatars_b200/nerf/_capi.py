@@ -13,7 +13,7 @@ NFB_PREC_FAST, NFB_PREC_EXACT = 0, 1
 EXPORTS = ["nfb_version", "nfb_strerror", "nfb_last_cuda_error", "nfb_create", "nfb_destroy", "nfb_load_weights",
            "nfb_set_frame", "nfb_render_forward", "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace",
            "nfb_render_forward_train", "nfb_render_backward", "nfb_train_debug", "nfb_debug_schedule", "nfb_loss_mse_grad",
-           "nfb_adam_step", "nfb_repack", "nfb_frame_products", "nfb_sample_rays", "nfb_host_map_cdf"]
+           "nfb_adam_step", "nfb_adam_step_dev", "nfb_repack", "nfb_frame_products", "nfb_sample_rays", "nfb_host_map_cdf"]
 
 
 class NfbModelDims(C.Structure):
@@ -64,6 +64,13 @@ class NfbAdam(C.Structure):
                 ("grad_scale", C.c_float), ("reg_offset", C.c_longlong), ("reg_weight", C.c_float)]
 
 
+class NfbAdamDev(C.Structure):
+    _fields_ = [("step", C.c_int32), ("pad", C.c_int32), ("lr0", C.c_float), ("decay_factor", C.c_float), ("decay_steps", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("grad_scale", C.c_float), ("reg_weight", C.c_float),
+                ("table_offset", C.c_longlong), ("row", C.c_void_p), ("lr_over_bc1", C.c_float), ("sqrt_bc2", C.c_float),
+                ("reg_offset", C.c_longlong)]
+
+
 class NfbRayMap(C.Structure):
     _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("bbox", C.c_int32 * 4), ("q_out", C.c_double), ("q_in", C.c_double)]
 
@@ -100,6 +107,7 @@ def _load():
     lib.nfb_loss_mse_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]
     lib.nfb_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(NfbAdam), C.c_void_p]
+    lib.nfb_adam_step_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
     lib.nfb_repack.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
     lib.nfb_frame_products.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -111,7 +119,7 @@ def _load():
     lib.nfb_host_linspace.argtypes = [C.POINTER(C.c_float), C.c_int]
     for fn in ("nfb_create", "nfb_destroy", "nfb_load_weights", "nfb_set_frame", "nfb_render_forward",
                "nfb_render_frame_host", "nfb_launch_count", "nfb_host_linspace", "nfb_render_forward_train",
-               "nfb_render_backward", "nfb_train_debug", "nfb_loss_mse_grad", "nfb_adam_step", "nfb_repack", "nfb_frame_products",
+               "nfb_render_backward", "nfb_train_debug", "nfb_loss_mse_grad", "nfb_adam_step", "nfb_adam_step_dev", "nfb_repack", "nfb_frame_products",
                "nfb_sample_rays", "nfb_host_map_cdf"):
         getattr(lib, fn).restype = C.c_int
     return lib

@@ -208,6 +208,12 @@ class Renderer:
         capi.check(capi.lib.nfb_adam_step(self._h, _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(),
                                           C.byref(hp), _stream()), "adam_step")
 
+    def adam_step_dev(self, params, grads, exp_avg, exp_avg_sq, dev_state):
+        """nfb_adam_step_dev: like adam_step with step counter / LR schedule / regularised row in the device struct `dev_state`
+        (a uint8 CUDA tensor holding an NfbAdamDev) — capturable in a CUDA graph."""
+        capi.check(capi.lib.nfb_adam_step_dev(self._h, _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(),
+                                              _ptr(dev_state), _stream()), "adam_step_dev")
+
     def repack(self, params_c, params_f):
         """nfb_repack: both networks' FP32 parameter tensors (lists in PARAM_ORDER) -> kernel-layout streams, one launch."""
         pc = (C.c_void_p * 26)(*[t.data_ptr() for t in params_c])

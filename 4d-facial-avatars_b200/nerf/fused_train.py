@@ -130,6 +130,74 @@ class FusedTrainer:
         eng.repack(self._pc, self._pf)
         eng.mark_synced(self.mc, self.mf)
 
+    # ---- the whole iteration as ONE CUDA graph (launch-bound at small per-rank batches: ~20 kernels of 3-800 us)
+    def capture(self, n, has_background=True, world=1, n_total=None, group=None):
+        """Capture gradients() + update() for batches of exactly n rays on this rank into a CUDA graph.  Everything that changes
+        from step to step lives in device memory: the inputs (static buffers filled by step_graph), the latent row index, and the
+        optimizer's step counter / learning rate (nfb_adam_step_dev).  The noise is drawn inside the graph (torch's graph-safe
+        Philox state), in the reference's order.  With world > 1 the NCCL all-reduce of the flat bucket is part of the graph."""
+        import ctypes as C
+        from . import _capi as capi
+        dev, eng, o = self.dev, self.eng, self.opts
+        n_total = n * world if n_total is None else n_total
+        z = lambda *shape, dt=torch.float32: torch.zeros(shape, device=dev, dtype=dt)  # noqa: E731
+        sb = dict(ro=z(n, 3), rd=z(n, 3), tgt=z(n, 3), bg=z(n, 3) if has_background else None, expr=z(76), idx=z(1, dt=torch.int64),
+                  lat=z(32), glat=z(32), g0=z(n, 3), g1=z(n, 3))
+        sb["rd"][:, 2] = -1.0  # a valid ray for the warm-up
+        st = capi.NfbAdamDev(step=self.iter, pad=0, lr0=self.lr0, decay_factor=self.decay_factor, decay_steps=self.decay_steps,
+                             beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=1.0, reg_weight=self.latent_reg,
+                             table_offset=self.lat_off if self.latent_reg > 0.0 else -1, row=sb["idx"].data_ptr(),
+                             lr_over_bc1=0.0, sqrt_bc2=1.0, reg_offset=-1)
+        sb["adam"] = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(dev)
+        has_fine = o["num_fine"] > 0
+        table_grads = self.grads[self.lat_off:].view(-1, 32)
+
+        def forward_backward():
+            sb["lat"].copy_(self.latent_codes.index_select(0, sb["idx"])[0])
+            eng.set_frame(sb["expr"], sb["lat"])
+            out = eng.render(sb["ro"], sb["rd"], o["near"], o["far"], o["num_coarse"], o["num_fine"], perturb=o["perturb"],
+                             noise_std=o["noise_std"], white_bkgd=o["white_bkgd"], background=sb["bg"], noise=self._draw_noise(n),
+                             precision=o["precision"], train=True)
+            self.loss.zero_()
+            eng.loss_mse_grad(out["rgb_coarse"], out["rgb_fine"] if has_fine else None, sb["tgt"], n_total, sb["g0"],
+                              sb["g1"] if has_fine else None, self.loss)
+            eng.backward_into((sb["g0"], None, None, sb["g1"] if has_fine else None, None, None, None), self._pc, self._pf, self._gc,
+                              self._gf, sb["glat"])
+            table_grads.index_add_(0, sb["idx"], sb["glat"][None])
+            return out
+
+        forward_backward()          # eager warm-up: sizes the library's training buffers (cudaMalloc is not capturable)
+        self.grads.zero_()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            keep = forward_backward()
+            if world > 1:
+                dist.all_reduce(self.grads, group=group)
+            eng.adam_step_dev(self.params, self.grads, self.exp_avg, self.exp_avg_sq, sb["adam"])
+            eng.repack(self._pc, self._pf)
+        self._graph = dict(graph=graph, sb=sb, n=n, keep=keep)
+        return self
+
+    def step_graph(self, ray_origins, ray_directions, target, expressions, latent_index, background=None):
+        """One optimizer step by replaying the captured graph (capture() first): copies the step's inputs into the static buffers —
+        on the current stream, so the caller may keep them on the device or in pinned host memory — and replays."""
+        g = self._graph
+        sb = g["sb"]
+        if ray_origins.shape[0] != g["n"]:
+            raise ValueError(f"the graph was captured for {g['n']} rays per step")
+        sb["ro"].copy_(ray_origins, non_blocking=True)
+        sb["rd"].copy_(ray_directions, non_blocking=True)
+        sb["tgt"].copy_(target, non_blocking=True)
+        if sb["bg"] is not None:
+            sb["bg"].copy_(background, non_blocking=True)
+        sb["expr"].copy_(expressions.reshape(-1), non_blocking=True)
+        sb["idx"].fill_(int(latent_index))
+        g["graph"].replay()
+        self.iter += 1
+        self.eng.mark_synced(self.mc, self.mf)
+        return self.loss[:2]
+
     def step(self, *args, **kwargs):
         """One optimizer step: gradients(...) then update().  Returns gradients()'s loss tensor."""
         loss = self.gradients(*args, **kwargs)

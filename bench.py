@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip rows / train / gpu_baseline / exact / stress records")
     ap.add_argument("--train-impl", default=os.environ.get("NFB_TRAIN_IMPL", "fused"), choices=["fused", "dropin"])
+    ap.add_argument("--no-train-graph", action="store_true", help="fused training step launch by launch instead of one CUDA graph replay")
     return ap.parse_args()
 
 
@@ -320,7 +321,7 @@ def bench_rows(c, H, W, nc, nf, steps, warmup, precision):
     return rec
 
 
-def bench_train(c, steps, warmup, impl, rays=2048, nc=64, nf=64):
+def bench_train(c, steps, warmup, impl, rays=2048, nc=64, nf=64, graph=True):
     """BASELINE config 3 (shipped YAML train block): 2048 rays of one 512x512 frame per iteration, 64c+64f, perturb + sigma
     noise 0.1, loss = mse(rgb_c) + mse(rgb_f) + 0.005*|latent|, Adam lr 5e-4 with the YAML's LR decay; with N ranks the batch is
     sharded (2048/N rays per rank) and ONE flat FP32 gradient bucket is all-reduced per iteration."""
@@ -348,10 +349,20 @@ def bench_train(c, steps, warmup, impl, rays=2048, nc=64, nf=64):
                                       num_coarse=nc, num_fine=nf, perturb=True, noise_std=0.1, near=NEAR, far=FAR,
                                       latent_reg=0.005)
 
+        captured = {"shard": None}
+
         def step(i, shard, ev=None):
             w, r = (world, rank) if shard else (1, 0)
             per = rays // w
             sel = idx[i][r * per:(r + 1) * per]
+            if graph:  # the whole iteration (incl. the all-reduce) is ONE graph replay; re-captured when the shard size changes
+                if captured["shard"] != shard:
+                    tr.capture(per, has_background=True, world=w, n_total=rays)
+                    captured["shard"] = shard
+                if ev is not None:
+                    ev[0].record()
+                    ev[1].record()
+                return tr.step_graph(ro[sel], rd[sel], target_img[sel], expr, 3, background=bg[sel])
             return tr.step(ro[sel], rd[sel], target_img[sel], expr, latent_index=3, background=bg[sel],
                            world=w, n_total=rays, events=ev)
     else:
@@ -400,14 +411,15 @@ def bench_train(c, steps, warmup, impl, rays=2048, nc=64, nf=64):
     t1, _, loss1 = run(max(5, min(steps, 20)), k, False)
     k += max(5, min(steps, 20))
     rec = {"workload": f"{rays} rays/iter of one 512x512 frame, {nc}c+{nf}f, perturb + noise 0.1, mse x2 + latent reg, Adam",
-           "impl": impl, "scaling": "strong", "t1_ms": t1, "rays_per_s_1gpu": rays / (t1 * 1e-3)}
+           "impl": impl + (" + CUDA graph (one replay per iteration, all-reduce inside)" if (impl == "fused" and graph) else ""),
+           "scaling": "strong", "t1_ms": t1, "rays_per_s_1gpu": rays / (t1 * 1e-3)}
     if world > 1:
         for j in range(max(3, warmup)):
             step(k, True); k += 1  # noqa: E702
         tn, coll, lossn = run(max(5, min(steps, 20)), k, True)
         tn_max = max_over_ranks(c, tn)
         rec.update({"ms_per_step": tn_max, "rays_per_s": rays / (tn_max * 1e-3), "efficiency_vs_1gpu": t1 / (world * tn_max),
-                    "collective_ms": coll, "rays_per_rank": rays // world, "loss_last": lossn})
+                    "collective_ms": None if (impl == "fused" and graph) else coll, "rays_per_rank": rays // world, "loss_last": lossn})
     else:
         rec.update({"ms_per_step": t1, "rays_per_s": rays / (t1 * 1e-3), "efficiency_vs_1gpu": 1.0, "collective_ms": 0.0,
                     "rays_per_rank": rays, "loss_last": loss1})
@@ -570,7 +582,7 @@ def main():
         extras["rows"] = bench_rows(c, 512, 512, 64, 128, a.steps, a.warmup, a.precision)
         extras["rows_1024"] = bench_rows(c, 1024, 1024, 128, 256, max(3, min(a.steps, 5)), 1, a.precision)
         try:
-            extras["train"] = bench_train(c, a.steps, a.warmup, a.train_impl)
+            extras["train"] = bench_train(c, a.steps, a.warmup, a.train_impl, graph=not a.no_train_graph)
         except Exception as e:  # a training-path failure must not take the headline down
             extras["train"] = {"unavailable": repr(e)[:300]}
             if world > 1:

@@ -217,6 +217,22 @@ typedef struct {
 int nfb_adam_step(NfbHandle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, const NfbAdam* hp,
                   void* stream);
 
+/* nfb_adam_step with its per-step scalars in DEVICE memory, so that a whole training iteration can be captured once in a CUDA graph
+ * and replayed: `dev_state` points to an NfbAdamDev on the device.  Each call first advances `step` and evaluates the reference's
+ * learning-rate schedule lr0 * decay_factor ^ ((i - 1) / decay_steps) for loop index i = step - 1 >= 1 (train_transformed_rays.py:393-399)
+ * and the bias corrections on the device (1 thread, float64), then runs the Adam kernel.  The regularised row is
+ * table_offset + 32 * row[0] (row = device pointer to the current latent index; table_offset < 0: no regulariser).  2 launches. */
+typedef struct {
+  int32_t step, pad;               /* in/out: steps taken so far (start at 0) */
+  float lr0, decay_factor, decay_steps, beta1, beta2, eps, grad_scale, reg_weight;
+  long long table_offset;
+  const long long* row;
+  float lr_over_bc1, sqrt_bc2;     /* out: this step's scalars (written by the prepare kernel) */
+  long long reg_offset;            /* out */
+} NfbAdamDev;
+int nfb_adam_step_dev(NfbHandle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, NfbAdamDev* dev_state,
+                      void* stream);
+
 /* nfb_load_weights for both networks at once (params_fine may be NULL), two launches (FP64 fold, pack): the re-pack after an
  * optimizer step. */
 int nfb_repack(NfbHandle* h, const float* const params_coarse[26], const float* const params_fine[26], void* stream);

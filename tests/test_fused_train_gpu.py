@@ -248,3 +248,39 @@ def test_training_over_the_memory_budget_runs_in_chunks(env, monkeypatch):
         assert float((a - b).abs().max()) < 1e-5   # the evaluation kernel renders what the training forward renders
     for a, b in zip(g1, g2):
         assert float((a - b).abs().max()) <= 3e-3 * max(float(a.abs().max()), 1e-12)
+
+
+def test_captured_graph_step_matches_the_eager_fused_step(env):
+    """FusedTrainer.capture(): the whole iteration (frame fold, noise draws, SAVE forward, loss, backward, Adam with device-side
+    step / LR schedule / regularised row, re-pack) replayed as ONE CUDA graph follows the eager fused loop: same losses, same
+    parameters after one step (to 1e-6; later steps are chaotic at |g| < eps, see above), device step counter in lock-step."""
+    nerf, _engine, fused_train, dev = env
+    steps, n, lat = 4, 64, 2
+    fr, ro, rd, bg, tgt, idx = _batches(dev, steps, n)
+    expr = fr["expr"].to(dev)
+    mk = lambda: fused_train.FusedTrainer(make_model(nerf, O.random_init_params(100), dev), make_model(nerf, O.random_init_params(101), dev),  # noqa: E731
+                                          n_latent=8, lr=5e-4, lr_decay_steps=250.0, lr_decay_factor=0.1, num_coarse=64, num_fine=64,
+                                          perturb=True, noise_std=0.1)
+    ta, tb = mk(), mk()
+    tb.capture(n)
+    eng = _engine.renderer_for(dev)
+    for i in range(steps):
+        sel = idx[i]
+        torch.manual_seed(500 + i)
+        la = ta.step(ro[sel], rd[sel], tgt[sel], expr, lat, background=bg[sel]).clone()
+        torch.manual_seed(500 + i)
+        l0 = eng.launch_count()
+        lb = tb.step_graph(ro[sel], rd[sel], tgt[sel], expr, lat, background=bg[sel]).clone()
+        torch.cuda.synchronize()
+        assert eng.launch_count() == l0  # no library call outside the graph
+        assert float((la - lb).abs().max()) < 2e-6, (i, la, lb)
+        if i == 0:
+            assert float((ta.params - tb.params).abs().max()) <= 1e-6
+    import ctypes as C
+    from nerf import _capi
+    st = _capi.NfbAdamDev.from_buffer_copy(bytes(tb._graph["sb"]["adam"].cpu().numpy().tobytes()))
+    assert st.step == steps == tb.iter and st.reg_offset == tb.lat_off + 32 * lat
+    lr_expected = 5e-4 * 0.1 ** ((steps - 2) / 250.0)
+    bc1 = 1.0 - 0.9 ** steps
+    assert abs(st.lr_over_bc1 - lr_expected / bc1) < 1e-9
+    assert float(tb.latent_codes[lat].abs().max()) > 0 and float(tb.latent_codes[lat + 1].abs().max()) == 0.0
