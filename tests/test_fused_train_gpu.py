@@ -253,14 +253,18 @@ def test_training_over_the_memory_budget_runs_in_chunks(env, monkeypatch):
 def test_captured_graph_step_matches_the_eager_fused_step(env):
     """FusedTrainer.capture(): the whole iteration (frame fold, noise draws, SAVE forward, loss, backward, Adam with device-side
     step / LR schedule / regularised row, re-pack) replayed as ONE CUDA graph follows the eager fused loop: same losses, same
-    parameters after one step (to 1e-6; later steps are chaotic at |g| < eps, see above), device step counter in lock-step."""
+    parameters after one step (to 1e-6; later steps are chaotic at |g| < eps, see above), device step counter in lock-step.
+    Deterministic sampling here: inside a graph torch's Philox offsets advance per replay, not per call, so a seeded replay does
+    not draw the numbers the seeded eager calls draw (same distribution); the stochastic graph is exercised at the end."""
     nerf, _engine, fused_train, dev = env
     steps, n, lat = 4, 64, 2
     fr, ro, rd, bg, tgt, idx = _batches(dev, steps, n)
     expr = fr["expr"].to(dev)
-    mk = lambda: fused_train.FusedTrainer(make_model(nerf, O.random_init_params(100), dev), make_model(nerf, O.random_init_params(101), dev),  # noqa: E731
+    mk = lambda: fused_train.FusedTrainer(  # noqa: E731
+        make_model(nerf, O.random_init_params(100), dev), make_model(nerf, O.random_init_params(101), dev),  # noqa: E731
                                           n_latent=8, lr=5e-4, lr_decay_steps=250.0, lr_decay_factor=0.1, num_coarse=64, num_fine=64,
-                                          perturb=True, noise_std=0.1)
+                                          perturb=noisy, noise_std=0.1 if noisy else 0.0)
+    noisy = False
     ta, tb = mk(), mk()
     tb.capture(n)
     eng = _engine.renderer_for(dev)
@@ -284,3 +288,10 @@ def test_captured_graph_step_matches_the_eager_fused_step(env):
     bc1 = 1.0 - 0.9 ** steps
     assert abs(st.lr_over_bc1 - lr_expected / bc1) < 1e-9
     assert float(tb.latent_codes[lat].abs().max()) > 0 and float(tb.latent_codes[lat + 1].abs().max()) == 0.0
+    noisy = True
+    tc = mk()
+    tc.capture(n)
+    ls = [tc.step_graph(ro[idx[i]], rd[idx[i]], tgt[idx[i]], expr, lat, background=bg[idx[i]]).clone() for i in range(steps)]
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v).all() and 0.01 < float(v.sum()) < 1.0 for v in ls)
+    assert float((ls[0] - ls[1]).abs().max()) > 0  # fresh noise on every replay
