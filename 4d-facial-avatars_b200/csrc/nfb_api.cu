@@ -656,7 +656,12 @@ int nfb_debug_schedule(int which, int index, uint32_t* out, int out_words) {
     case 1: return nfb::debug_prog_v6(index, out);
     case 2: return nfb::debug_prog_chain(index, out);
     case 3: return nfb::debug_jobs_dw(index, out);
-    default: return -1;
+    default:
+      if (which >= 1000) {  // 1000 + n_iter * 100 + Tc * 10 + Tf: the pipelined kernel's job sequence
+        const int w = which - 1000;
+        return nfb::debug_jobs_v7(w / 100, (w / 10) % 10, w % 10, index, out);
+      }
+      return -1;
   }
 }
 

@@ -88,6 +88,7 @@ struct DwParams {
 // host copies of the compile-time schedules (nfb_debug_schedule); index < 0: number of entries; else words written or -1
 int debug_prog_v4(int index, uint32_t* out);
 int debug_prog_v6(int index, uint32_t* out);
+int debug_jobs_v7(int n_iter, int tc, int tf, int index, uint32_t* out);
 int debug_prog_chain(int index, uint32_t* out);
 int debug_jobs_dw(int index, uint32_t* out);
 cudaError_t train_kernels_setup();

@@ -81,8 +81,8 @@ static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory li
 
 struct JobIt {
   int n_iter, Tc, Tf, blk, pass, t;
-  __device__ __forceinline__ JobIt(int n, int tc, int tf) : n_iter(n), Tc(tc), Tf(tf), blk(-1), pass(0), t(-1) {}
-  __device__ __forceinline__ bool next() {
+  __host__ __device__ __forceinline__ JobIt(int n, int tc, int tf) : n_iter(n), Tc(tc), Tf(tf), blk(-1), pass(0), t(-1) {}
+  __host__ __device__ __forceinline__ bool next() {
     ++t;
     for (;;) {
       if (pass == 0) {
@@ -94,7 +94,7 @@ struct JobIt {
       if (blk >= n_iter) return false;
     }
   }
-  __device__ __forceinline__ int unit() const { return pass == 0 ? blk + 1 : blk; }
+  __host__ __device__ __forceinline__ int unit() const { return pass == 0 ? blk + 1 : blk; }
 };
 
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -755,6 +755,19 @@ __global__ void __launch_bounds__(kThreads, 1) render3_kernel(const __grid_const
 }
 
 }  // namespace v7
+
+// host copy of the pipelined kernel's job sequence (tests): job `index` of a CTA with n_iter units, Tc / Tf tile pairs per pass ->
+// (unit iteration, pass, tile); index < 0: the number of jobs; also the kernel's shared-memory size and per-stream row limits
+int debug_jobs_v7(int n_iter, int tc, int tf, int index, uint32_t* out) {
+  int k = 0;
+  for (v7::JobIt j(n_iter, tc, tf); j.next(); ++k)
+    if (k == index) {
+      out[0] = (uint32_t)j.unit(); out[1] = (uint32_t)j.pass; out[2] = (uint32_t)j.t;
+      out[3] = (uint32_t)v7::kSmemBytes; out[4] = (uint32_t)v7::kRowsC; out[5] = (uint32_t)v7::kRowsF; out[6] = (uint32_t)v7::kSortMax;
+      return 7;
+    }
+  return index < 0 ? k : -1;
+}
 
 cudaError_t render3_kernel_setup() {
   cudaError_t e = cudaFuncSetAttribute(v7::render3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::kSmemBytes);

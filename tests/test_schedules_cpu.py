@@ -120,3 +120,30 @@ def test_weight_gradient_jobs(lib):
     biased = [j[5] for j in jobs if j[5] < (1 << 31)]
     assert sorted(set(biased)) == list(range(9))                         # every layer's bias is produced ...
     assert len([b for b in biased if b <= 5]) == 12                      # ... by both halves of the 256-wide layers, once each
+
+
+@pytest.mark.parametrize("n_iter,tc,tf", [(1, 1, 3), (2, 1, 3), (5, 1, 3), (4, 1, 2), (3, 1, 1)])
+def test_pipelined_kernel_job_sequence(lib, n_iter, tc, tf):
+    """csrc/nfb_render3.cu: every role of the pipelined kernel walks C(0) | C(1) F(0,.) | C(2) F(1,.) | ...  Invariants the
+    hand-offs rely on: every (unit, pass, tile) exactly once; the coarse pass of unit u+1 is issued BEFORE the fine pass of unit u
+    (so the sampler resamples u while the tensor core runs C(u+1)) but never two coarse passes ahead (the per-unit buffers are
+    double-buffered by unit parity, three ray-constant slots); tiles of a pass in order; the shared-memory map fits 227 KB."""
+    which = 1000 + 100 * n_iter + 10 * tc + tf
+    jobs = [tuple(e[:3]) for e in entries(lib, which)]
+    extra = entries(lib, which)[0][3:7]
+    assert extra[0] <= 232448 and extra[1] == 128 and extra[2] == 384 and extra[3] >= 2 * extra[2]
+    assert len(jobs) == n_iter * (tc + tf) and len(set(jobs)) == len(jobs)
+    pos = {j: k for k, j in enumerate(jobs)}
+    for u in range(n_iter):
+        for t in range(tc):
+            assert (u, 0, t) in pos
+            if t:
+                assert pos[(u, 0, t)] == pos[(u, 0, t - 1)] + 1
+        for t in range(tf):
+            assert pos[(u, 1, t)] > pos[(u, 0, tc - 1)]                       # fine after its own coarse pass
+            if t:
+                assert pos[(u, 1, t)] == pos[(u, 1, t - 1)] + 1
+        if u + 1 < n_iter:
+            assert pos[(u + 1, 0, 0)] < pos[(u, 1, 0)]                        # C(u+1) before F(u, 0)
+        if u + 2 < n_iter:
+            assert pos[(u + 2, 0, 0)] > pos[(u, 1, tf - 1)]                   # ... but C(u+2) only after F(u) has been issued
