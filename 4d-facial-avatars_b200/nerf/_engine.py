@@ -56,6 +56,7 @@ class Renderer:
         self._h = h
         self._lin = {}
         self._plist = {}
+        self.packed_owner = None   # the FusedTrainer whose weights the packed streams hold (None: whatever sync_weights packed last)
         self._versions = [None, None]
         self._keep = [None, None]  # contiguous FP32 copies handed to the pack kernels
         self.train_token = 0       # bumped by every training forward: the handle keeps ONE saved state
@@ -94,6 +95,7 @@ class Renderer:
             tensors = [_f32c(t, self.device) for t in self._params(model)]
             arr = (C.c_void_p * 26)(*[t.data_ptr() for t in tensors])
             capi.check(capi.lib.nfb_load_weights(self._h, which, arr, _stream()), "load_weights")
+            self.packed_owner = None
             self._keep[which] = tensors
             self._versions[which] = fp
 

@@ -60,8 +60,15 @@ class FusedTrainer:
         self._gf = [None if s else g for s, g in zip(skip, self._gviews[npar:])] if model_fine is not None else None
         self.loss = torch.zeros(4, device=dev, dtype=torch.float32)
         self._g_rgb = {}
-        self.eng.repack(self._pc, self._pf)
-        self.eng.mark_synced(model_coarse, model_fine)
+        self._own_engine()
+
+    def _own_engine(self):
+        """The device's renderer holds ONE set of packed weights: (re-)pack this trainer's if someone else's are in place (another
+        trainer, or other models rendered through the drop-in API since the last step)."""
+        if self.eng.packed_owner is not self:
+            self.eng.repack(self._pc, self._pf)
+            self.eng.mark_synced(self.mc, self.mf)
+            self.eng.packed_owner = self
 
     def lr(self):
         """Learning rate of step number self.iter (1-based).  The reference assigns lr0 * factor ** (i / decay) AFTER the
@@ -94,6 +101,7 @@ class FusedTrainer:
         which every rank holds the whole batch's gradient.  Returns the device tensor [mse_coarse, mse_fine] of THIS shard's
         share (sum over ranks = batch loss).  `events`: optional (before_collective, after_collective) CUDA events."""
         eng, o = self.eng, self.opts
+        self._own_engine()
         n = ray_origins.shape[0]
         n_total = n * world if n_total is None else n_total
         row = self.latent_codes[latent_index]
@@ -129,6 +137,7 @@ class FusedTrainer:
                       reg_offset=self.lat_off + 32 * self._reg_row if self.latent_reg > 0.0 else -1, reg_weight=self.latent_reg)
         eng.repack(self._pc, self._pf)
         eng.mark_synced(self.mc, self.mf)
+        eng.packed_owner = self
 
     # ---- the whole iteration as ONE CUDA graph (launch-bound at small per-rank batches: ~20 kernels of 3-800 us)
     def capture(self, n, has_background=True, world=1, n_total=None, group=None):
@@ -166,6 +175,7 @@ class FusedTrainer:
             table_grads.index_add_(0, sb["idx"], sb["glat"][None])
             return out
 
+        self._own_engine()
         forward_backward()          # eager warm-up: sizes the library's training buffers (cudaMalloc is not capturable)
         self.grads.zero_()
         torch.cuda.synchronize()
@@ -186,6 +196,7 @@ class FusedTrainer:
         sb = g["sb"]
         if ray_origins.shape[0] != g["n"]:
             raise ValueError(f"the graph was captured for {g['n']} rays per step")
+        self._own_engine()
         sb["ro"].copy_(ray_origins, non_blocking=True)
         sb["rd"].copy_(ray_directions, non_blocking=True)
         sb["tgt"].copy_(target, non_blocking=True)
@@ -196,6 +207,7 @@ class FusedTrainer:
         g["graph"].replay()
         self.iter += 1
         self.eng.mark_synced(self.mc, self.mf)
+        self.eng.packed_owner = self
         return self.loss[:2]
 
     def step(self, *args, **kwargs):
