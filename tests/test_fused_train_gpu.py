@@ -273,6 +273,7 @@ def test_captured_graph_step_matches_the_eager_fused_step(env):
         torch.manual_seed(500 + i)
         la = ta.step(ro[sel], rd[sel], tgt[sel], expr, lat, background=bg[sel]).clone()
         torch.manual_seed(500 + i)
+        tb._own_engine()  # two trainers alternate on the device's one renderer here: ta's step left ITS weights packed
         l0 = eng.launch_count()
         lb = tb.step_graph(ro[sel], rd[sel], tgt[sel], expr, lat, background=bg[sel]).clone()
         torch.cuda.synchronize()
