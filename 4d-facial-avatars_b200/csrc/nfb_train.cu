@@ -531,34 +531,49 @@ struct Job {
   int bias_layer;             // >= 0: also accumulate column sums of A into the bias of this layer
   int out_off, out_ld, out_row0;
 };
-// Jobs are dealt to kGroups groups of CTAs of roughly equal tensor-core work; within a group every CTA runs the group's
-// jobs over its own share of the tiles (fewer accumulator drains and atomics than every CTA running every job).
+// Jobs are dealt to kGroups groups of CTAs; within a group every CTA runs the group's jobs over its own share of the tiles (fewer
+// accumulator drains and atomics than every CTA running every job).  The kernel is HBM-bound (each job streams its two images of
+// every tile once), so the groups are balanced by BYTES per tile (172..200 KB each), and groups 2q / 2q+1 are the two
+// 128-feature output halves of the SAME layers in the SAME order: they run on neighbouring CTAs over the same tiles at the same
+// time, so the B image both need (the layer's whole input, 2/3 of a job's bytes) comes from HBM once and from L2 the second time.
 constexpr int kNumJobs = 21;
-constexpr int kGroups = 4;
+constexpr int kGroups = 8;
 struct JobTable { Job j[kNumJobs]; int group_begin[kGroups + 1]; };
+constexpr Job half_job(int dy_layer, int h, int b_off, int b_rows, int bias_layer, int out_off) {
+  return Job{rec_dy_off(dy_layer), 256, h, b_off, b_rows, bias_layer, out_off, b_rows, 128 * h};
+}
 constexpr JobTable make_jobs() {
   JobTable t{};
-  int i = 0;
-  t.group_begin[0] = i;
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(1), 256, h, rec_x_off(0), 256, 1, kAcc1, 256, 128 * h};
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(2), 256, h, rec_x_off(1), 256, 2, kAcc2, 256, 128 * h};
-  t.group_begin[1] = i;
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(4), 256, h, rec_x_off(3), 256, 4, kAcc4, 256, 128 * h};
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(5), 256, h, rec_x_off(4), 256, 5, kAcc5, 256, 128 * h};
-  t.group_begin[2] = i;
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(3), 256, h, rec_x_off(2), 256, -1, kAcc3b, 256, 128 * h};
-  t.j[i++] = Job{rec_dy_off(6), 128, 0, rec_x_off(5), 256, 6, kAcc6, 256, 0};   // d M1
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(0), 256, h, kRecPE, 64, 0, kAcc0, 64, 128 * h};  // layers_xyz.0: dY0 x PE
-  t.group_begin[3] = i;
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_dy_off(3), 256, h, kRecPE, 64, 3, kAcc3a, 64, 128 * h};
-  t.j[i++] = Job{rec_dy_off(6), 128, 0, kRecPEd, 32, -1, kAcc6d, 32, 0};         // d layers_dir.0[:, 256:280]
-  for (int h = 0; h < 2; ++h) t.j[i++] = Job{rec_x_off(5), 256, h, kRecDRaw, 16, -1, kAccSig, 16, 128 * h};  // h5^T . d raw
+  int i = 0, g = 0;
+  for (int h = 0; h < 2; ++h) {  // groups 0, 1: layers_xyz.1, .2
+    t.group_begin[g++] = i;
+    t.j[i++] = half_job(1, h, rec_x_off(0), 256, 1, kAcc1);
+    t.j[i++] = half_job(2, h, rec_x_off(1), 256, 2, kAcc2);
+  }
+  for (int h = 0; h < 2; ++h) {  // groups 2, 3: layers_xyz.4, .5
+    t.group_begin[g++] = i;
+    t.j[i++] = half_job(4, h, rec_x_off(3), 256, 4, kAcc4);
+    t.j[i++] = half_job(5, h, rec_x_off(4), 256, 5, kAcc5);
+  }
+  for (int h = 0; h < 2; ++h) {  // groups 4, 5: the skip layer (hidden part, then its PE part) and layers_xyz.0 (dY0 x PE)
+    t.group_begin[g++] = i;
+    t.j[i++] = half_job(3, h, rec_x_off(2), 256, -1, kAcc3b);
+    t.j[i++] = half_job(3, h, kRecPE, 64, 3, kAcc3a);
+    t.j[i++] = half_job(0, h, kRecPE, 64, 0, kAcc0);
+  }
+  t.group_begin[g++] = i;          // group 6: everything that reads dY6 or h5
+  t.j[i++] = Job{rec_dy_off(6), 128, 0, rec_x_off(5), 256, 6, kAcc6, 256, 0};     // d M1
+  t.j[i++] = Job{rec_dy_off(6), 128, 0, kRecPEd, 32, -1, kAcc6d, 32, 0};          // d layers_dir.0[:, 256:280]
+  t.j[i++] = Job{rec_x_off(5), 256, 0, kRecDRaw, 16, -1, kAccSig, 16, 0};         // h5^T . d raw, first half
+  t.group_begin[g++] = i;          // group 7: its second half and the rest of the direction branch
+  t.j[i++] = Job{rec_x_off(5), 256, 1, kRecDRaw, 16, -1, kAccSig, 16, 128};
   t.j[i++] = Job{rec_dy_off(7), 128, 0, rec_x_off(6), 128, 7, kAcc7, 128, 0};
   t.j[i++] = Job{rec_dy_off(8), 128, 0, rec_x_off(7), 128, 8, kAcc8, 128, 0};
-  t.j[i++] = Job{rec_x_off(8), 128, 0, kRecDRaw, 16, -1, kAcc9, 16, 0};          // g2^T . d raw
-  t.group_begin[4] = i;
+  t.j[i++] = Job{rec_x_off(8), 128, 0, kRecDRaw, 16, -1, kAcc9, 16, 0};           // g2^T . d raw
+  t.group_begin[g] = i;
   return t;
 }
+static_assert(make_jobs().group_begin[kGroups] == kNumJobs, "job table");
 __constant__ JobTable c_jobs = make_jobs();
 
 __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__ DwParams p) {
@@ -924,7 +939,7 @@ cudaError_t launch_chain(const ChainParams& p, int num_sms, cudaStream_t st, lon
 cudaError_t launch_dw(const DwParams& p, int num_sms, cudaStream_t st, long long* launches) {
   const int total = p.n_units * p.t_cnt;
   if (total <= 0) return cudaSuccess;
-  int parts = num_sms / dw::kGroups;  // CTAs per job group (37 on a 148-SM B200)
+  int parts = num_sms / dw::kGroups;  // CTAs per job group (18 on a 148-SM B200: 144 CTAs)
   if (parts > total) parts = total;
   if (parts < 1) parts = 1;
   dw::dw_kernel<<<parts * dw::kGroups, dw::kThreads, dw::kSmemBytes, st>>>(p);

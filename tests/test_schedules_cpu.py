@@ -110,13 +110,23 @@ def test_weight_gradient_jobs(lib):
         bias_layer = bias_layer - (1 << 32) if bias_layer >= (1 << 31) else bias_layer   # -1 = no bias, sent as uint32
         assert 0 <= a_off and a_off + 2 * a_rows * 128 <= REC_BYTES and a_rows in (128, 256) and a_half * 128 < a_rows
         assert 0 <= b_off and b_off + 2 * b_rows * 128 <= REC_BYTES and b_rows in (16, 32, 64, 128, 256) and b_rows == out_ld
-        assert -1 <= bias_layer <= 8 and 0 <= group < 4
+        assert -1 <= bias_layer <= 8 and 0 <= group < 8
         lo = out_off + out_row0 * out_ld
         used.append((lo, lo + 128 * out_ld))
     used.sort()
     for (a0, a1), (b0, b1) in zip(used, used[1:]):
         assert a1 <= b0, "weight-gradient jobs overlap in the accumulator space"
     assert used[-1][1] <= ACC_FLOATS
+    # groups 2q / 2q+1 (q < 3) are the two output halves of the same layers in the same order: neighbouring CTAs stream the same
+    # B images of the same tiles at the same time (one HBM read, one L2 hit); per-tile bytes of the groups are balanced
+    by_group = [[j for j in jobs if j[9] == g] for g in range(8)]
+    for q in range(3):
+        lo, hi = by_group[2 * q], by_group[2 * q + 1]
+        assert len(lo) == len(hi) and len(lo) >= 2
+        for a, b in zip(lo, hi):
+            assert a[0] == b[0] and a[3] == b[3] and a[4] == b[4] and (a[2], b[2]) == (0, 1) and a[6] == b[6] and (a[8], b[8]) == (0, 128)
+    load = [sum(2 * 128 * (128 + j[4]) for j in grp) for grp in by_group]
+    assert max(load) <= 1.2 * min(load), load
     biased = [j[5] for j in jobs if j[5] < (1 << 31)]
     assert sorted(set(biased)) == list(range(9))                         # every layer's bias is produced ...
     assert len([b for b in biased if b <= 5]) == 12                      # ... by both halves of the 256-wide layers, once each
