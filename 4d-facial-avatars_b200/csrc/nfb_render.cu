@@ -40,6 +40,15 @@ namespace nfb {
 constexpr int kNumSlots = 5;    // ring of 32 KB weight units (exact mode uses 4: slot 4 holds the lo half of the PE operand)
 constexpr int kRowsMax = 512;   // sample rows of one pass of one unit of work
 constexpr int kThreads = 320;   // producer warp + MMA warp + 8 row warps
+// SAVE (training forward): 512 threads — warps 0/1 producer / MMA, 2..3 idle (setmaxnreg works on whole warpgroups), 4..11 the
+// row warps, 12..15 the RECORD SAVERS: one per TMEM lane quadrant, they read the FP16 activations the epilogue left in TMEM (the
+// next step's A operand) and write the transposed record images — ~2,200 two-byte stores per tile and warp that used to sit on
+// the row warps' critical path.  The MMA warp may not overwrite a region before its savers have read it (bar_saved).
+constexpr int kThreadsSave = 512;
+constexpr int kRegsLight = 80, kRegsRow = 176, kRegsSaver = 80;
+static_assert((4 * kRegsLight + 8 * kRegsRow + 4 * kRegsSaver) * 32 <= 65536, "register file");
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 #ifndef NFB_CLUSTER
 #define NFB_CLUSTER 2
 #endif
@@ -68,7 +77,7 @@ constexpr int kOffSort = kOffBins + kRowsMax * 4;
 constexpr int kOffDirBias = kOffSort + kRowsMax * 4;
 constexpr int kOffRay = kOffDirBias + 2 * 128 * 4;
 constexpr int kOffBars = kOffRay + 2 * kRayFloats * 4;
-constexpr int kNumBars = 2 * kNumSlots + 4;
+constexpr int kNumBars = 2 * kNumSlots + 4 + 6;  // + SAVE: bar_sv[2 halves][2 step parities], bar_saved[2 regions]
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kMaxProg = 40;                     // weight units per tile (32 with the current step table)
 constexpr int kSmemBytes = kOffTmemPtr + 16;
@@ -78,7 +87,10 @@ static_assert(kOffBias % 16 == 0 && kOffRaw % 16 == 0 && kOffBars % 8 == 0, "ali
 // far too slow for the issue loops):  x = instruction descriptor, y = accumulator column | A column << 16 (TMEM columns
 // relative to the allocation base), z = flags, w = (byte offset in the x1 weight stream) / 16 | rows << 20.
 enum : uint32_t {
-  kUnitFromPe = 1u, kUnitWait0 = 2u, kUnitWait1 = 4u, kUnitFirst = 8u, kUnitCommit0 = 16u, kUnitCommit1 = 32u, kUnitPostWait1 = 64u
+  kUnitFromPe = 1u, kUnitWait0 = 2u, kUnitWait1 = 4u, kUnitFirst = 8u, kUnitCommit0 = 16u, kUnitCommit1 = 32u, kUnitPostWait1 = 64u,
+  kUnitStepStart = 128u,  // first unit of its step (SAVE: the accumulator region must have been read by the record savers)
+  kUnitOddRegion = 256u,  // the step accumulates into region 1
+  kUnitSaved = 512u       // the step's output goes to the training record (steps 0..8)
 };
 constexpr int total_units() {
   int n = 0;
@@ -114,6 +126,9 @@ constexpr ProgTable make_prog() {
       if (ui.group == 2 && first_g2) flags |= kUnitWait1;
       if (first_of_half) flags |= kUnitFirst;
       if (ui.last) flags |= kUnitCommit0;                               // the step's accumulator is complete
+      if (u == 0) flags |= kUnitStepStart;
+      if (s & 1) flags |= kUnitOddRegion;
+      if (s <= 8) flags |= kUnitSaved;
       if (u == nu - 1 && !any_g2) flags |= kUnitPostWait1;           // still consume the half-1 "converted" signal
       const uint32_t d_col = region_col_c(s);
       const uint32_t a_col = (region_col_c(s) ^ 256u) + (uint32_t)(ui.ka - si.pe_first) * 64u;
@@ -155,7 +170,7 @@ __device__ __forceinline__ void epi_half(uint32_t t_slice, uint32_t bias, uint32
 
 // ------------------------------------------------------------------------------------------------
 template <bool EXACT, bool SAVE>
-__global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
+__global__ void __launch_bounds__(SAVE ? kThreadsSave : kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
   // Use the dynamic shared array directly (no integer round trip) so the compiler keeps the shared address
   // space and emits LDS/STS instead of generic loads; the swizzled operands need 1024-byte alignment.
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -169,6 +184,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
   const uint32_t bar_empty = bar_full + kNumSlots * 8;          // [kNumSlots]
   const uint32_t bar_aready = bar_empty + kNumSlots * 8;        // [2] half-h output of the previous step converted
   const uint32_t bar_accfull = bar_aready + 16;                 // [2] all MMAs of the current step completed ([0] used)
+  const uint32_t bar_sv = bar_accfull + 16;                     // SAVE [half][step & 1]: the step's FP16 output is in TMEM -> savers
+  const uint32_t bar_saved = bar_sv + 32;                       // SAVE [region]: the savers have read the region -> MMA warp
+  constexpr int kRow0 = SAVE ? 4 : 2;                           // first of the eight row warps
+  constexpr int NT = SAVE ? kThreadsSave : kThreads;
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
 
@@ -180,6 +199,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar_aready + h * 8, kRowThreads / 32);  // one arrival per row warp per step
       mbar_init(bar_accfull + h * 8, 1);
+      mbar_init(bar_sv + h * 16, kRowThreads / 32);
+      mbar_init(bar_sv + h * 16 + 8, kRowThreads / 32);
+      mbar_init(bar_saved + h * 8, 4);  // one arrival per saver warp
     }
     mbar_fence_init();
   }
@@ -187,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     tmem_alloc(smem_base + kOffTmemPtr, 512);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < kBiasFloats; i += kThreads) {
+  for (int i = threadIdx.x; i < kBiasFloats; i += NT) {
     bias_s[i] = p.bias[0][i];
     bias_s[kBiasFloats + i] = (p.nf > 0) ? p.bias[1][i] : 0.f;
   }
@@ -205,9 +227,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
   const int n_iter = (p.n_units - first_in_cluster + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tiles_per_unit = p.tiles_c + p.tiles_f;
 
+  // SAVE: every role re-partitions the register file first thing inside its own branch (whole warpgroups: 0..3, 4..11, 12..15);
+  // ptxas allocates each branch against the count set there.
   if (warp == 0) {
     // ============================== weight producer ==============================
     // The whole warp runs the (warp-uniform) loop; one elected lane issues the copies.
+    if constexpr (SAVE) reg_dec<kRegsLight>();
     {
       uint32_t slot = 0, phase = 0, seq = 0;
       PhaseTimer tm(p.prof, p.prof != nullptr && lane == 0);
@@ -238,8 +263,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     // Warp-uniform loop (all 32 lanes wait on the barriers); one elected lane issues tcgen05.mma / commit.
+    if constexpr (SAVE) reg_dec<kRegsLight>();
     {
       uint32_t slot = 0, phase = 0, ph_a0 = 0, ph_a1 = 0;
+      uint32_t sv_pending = 0, sv_phase = 0;  // SAVE, per region bit: a saved step lives there / parity of bar_saved
       PhaseTimer tm(p.prof, p.prof != nullptr && lane == 0);
       const bool prof_on = NFB_TIMERS && p.prof != nullptr;
       long long acc_gate = 0, acc_full = 0, acc_issue = 0, tq = prof_on ? clock64() : 0;
@@ -250,6 +277,18 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
           for (int i = 0; i < kTileUnits; ++i) {
             const ProgEntry e = c_prog.e[i];
             if (prof_on) { const long long tn = clock64(); acc_issue += tn - tq; tq = tn; }
+            if constexpr (SAVE) {
+              if (e.z & kUnitStepStart) {  // this step overwrites its region: the savers must be done with what lived there
+                const uint32_t rho = (e.z & kUnitOddRegion) ? 1u : 0u;
+                if (sv_pending & (1u << rho)) {
+                  mbar_wait(bar_saved + rho * 8, (sv_phase >> rho) & 1u);
+                  sv_phase ^= 1u << rho;
+                  sv_pending &= ~(1u << rho);
+                  tc_fence_after_sync();
+                }
+                if (e.z & kUnitSaved) sv_pending |= 1u << rho;
+              }
+            }
             if (e.z & kUnitWait0) {  // group-1 units: previous step's half-0 output (or the PE buffer) is in place
               mbar_wait(bar_aready, ph_a0);
               ph_a0 ^= 1;
@@ -305,12 +344,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         atomicAdd(p.prof + 46, (unsigned long long)acc_full);
       }
     }
-  } else {
+  } else if (warp >= kRow0 && warp < kRow0 + 8) {
     // ============================== row warps ==============================
+    if constexpr (SAVE) reg_inc<kRegsRow>();
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;     // tile row == TMEM lane
-    const int ch = (warp - 2) >> 2;    // which half of the columns this warp of the quadrant pair handles
-    const int ew = warp - 2;           // 0..7, ray index for per-ray stages
+    const int ch = (warp - kRow0) >> 2;  // which half of the columns this warp of the quadrant pair handles
+    const int ew = warp - kRow0;       // 0..7, ray index for per-ray stages
     const int etid = ch * 128 + row;   // 0..255
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint8_t* pe_hi = smem + kOffPeHi;
@@ -591,14 +631,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               tmem_wait_st();
               tc_fence_before_sync();
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar_aready);
+              if (lane == 0) {
+                mbar_arrive(bar_aready);
+                if constexpr (SAVE) mbar_arrive(bar_sv + (s & 1) * 8);  // s <= 8 here: the saver warps write the image
+              }
             }
-            if constexpr (SAVE) {  // after the gate: the record stores overlap the next step's MMAs
+            if constexpr (SAVE) {  // after the gate: the ReLU masks (the FP16 images are written by the saver warps)
               if (rec && s <= 8) {
                 const int c0 = 64 * ch;
-                uint8_t* img = rec + rec_x_off(s) + img_row_base(rec_width(s), row);
-                store_t32(img, row, c0, ha);
-                store_t32(img, row, c0 + 32, hb);
                 *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(rec + kRecMask) + (s * 128 + row) * 8 + (c0 >> 5)) = make_uint2(relu_mask32(ha), relu_mask32(hb));
               }
             }
@@ -618,14 +658,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
               tmem_wait_st();
               tc_fence_before_sync();
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar_aready + 8);
+              if (lane == 0) {
+                mbar_arrive(bar_aready + 8);
+                if constexpr (SAVE) { if (s <= 5) mbar_arrive(bar_sv + 16 + (s & 1) * 8); }
+              }
             }
             if constexpr (SAVE) {
               if (rec && s <= 5) {
                 const int c0 = 128 + 64 * ch;
-                uint8_t* img = rec + rec_x_off(s) + img_row_base(256, row);
-                store_t32(img, row, c0, ha);
-                store_t32(img, row, c0 + 32, hb);
                 *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(rec + kRecMask) + (s * 128 + row) * 8 + (c0 >> 5)) = make_uint2(relu_mask32(ha), relu_mask32(hb));
               }
             }
@@ -766,6 +806,62 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
       }  // pass
     }    // units
     tc_fence_before_sync();
+  } else if (SAVE && warp >= 12) {
+    // ============================== record savers (SAVE only) ==============================
+    // Warp 12 + q owns TMEM lanes [32q, 32q+32).  Step s (0..8) leaves its FP16 output in place in region (s & 1): features
+    // [64i, 64i+64) in the 32 columns at 64i.  bar_sv[half][s & 1] (two barriers per half, alternating by step) cannot run more than
+    // one phase ahead of this warp, because the step that next completes the same barrier is s + 2, whose MMAs wait for
+    // bar_saved of step s.
+    reg_dec<kRegsSaver>();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t sv_ph = 0;  // bit (half * 2 + parity): phase of bar_sv[half][parity]
+    for (int it = 0; it < n_iter; ++it) {
+      const int unit = blockIdx.x + it * gridDim.x;
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && p.nf == 0) break;
+        const int n_tiles = pass ? p.tiles_f : p.tiles_c;
+        for (int t = 0; t < n_tiles; ++t) {
+          uint8_t* rec = (unit < p.n_units) ? p.save_rec + (size_t)(unit * tiles_per_unit + (pass ? p.tiles_c : 0) + t) * kRecBytes : nullptr;
+#pragma unroll 1
+          for (int s = 0; s <= 8; ++s) {
+            const uint32_t par = (uint32_t)(s & 1);
+            const uint32_t t_reg = t_lane + region_col(s);
+            uint8_t* img = rec ? rec + rec_x_off(s) + img_row_base(rec_width(s), row) : nullptr;
+            const int n_slices = rec_width(s) >> 6;  // 64 features (32 TMEM columns) at a time
+#pragma unroll 1
+            for (int i = 0; i < n_slices; ++i) {
+              if ((i & 1) == 0) {  // slices 0, 1 belong to output half 0, slices 2, 3 to half 1
+                const int h = i >> 1;
+                const uint32_t bit = 1u << (h * 2 + par);
+                mbar_wait(bar_sv + h * 16 + par * 8, (sv_ph & bit) ? 1u : 0u);
+                sv_ph ^= bit;
+                tc_fence_after_sync();
+              }
+              uint32_t v[32];
+              tmem_ld32(t_reg + 64 * i, v);
+              tmem_wait_ld();
+              if (i == n_slices - 1) {  // the whole region has been read: the MMA warp may overwrite it
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_saved + par * 8);
+              }
+              if (img) {
+                uint32_t h0[16], h1[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { h0[j] = v[j]; h1[j] = v[16 + j]; }
+                store_t32(img, row, 64 * i, h0);
+                store_t32(img, row, 64 * i + 32, h1);
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before_sync();
+  } else if (SAVE) {
+    reg_dec<kRegsLight>();  // warps 2, 3: idle, but setmaxnreg is a warpgroup-wide instruction
   }
 
   __syncthreads();
@@ -801,7 +897,7 @@ cudaError_t launch_render(const RenderParams& p, int precision, int num_sms, cud
   if (grid > num_sms) grid = num_sms / kCluster * kCluster;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(p.save_rec != nullptr ? kThreadsSave : kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
