@@ -224,17 +224,24 @@ __host__ __device__ constexpr int bwd_unit_offset(int s, int u) { return bwd_ste
 namespace chain {
 
 constexpr int kNumSlots = 5;
-constexpr int kThreads = 320;
+// 512 threads: warp 0 weight producer, 1 MMA issuer, 2..3 idle (setmaxnreg works on whole warpgroups), 4..11 row warps,
+// 12..15 record savers — as in the training forward (nfb_render.cu), they read each step's FP16 output back from TMEM and write
+// the transposed dY image, so the ~1,900 two-byte stores per tile and warp are off the row warps' critical path.
+constexpr int kThreads = 512;
+constexpr int kRegsLight = 80, kRegsRow = 176, kRegsSaver = 80;
+static_assert((4 * kRegsLight + 8 * kRegsRow + 4 * kRegsSaver) * 32 <= 65536, "register file");
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int kCluster = 2;
 constexpr int kRowThreads = 256;
 constexpr int kOffRing = 0;
 constexpr int kOffOp = kOffRing + kNumSlots * kMaxUnitBytes;  // d raw operand: [128 rows x 64 k] FP16, swizzled (k < 4 used)
 constexpr int kOffBars = kOffOp + kTileM * 128;
-constexpr int kNumBars = 2 * kNumSlots + 4;
+constexpr int kNumBars = 2 * kNumSlots + 4 + 6;  // + bar_sv[2 halves][2 step parities], bar_saved[2 regions]
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 
-enum : uint32_t { kFromOp = 1u, kWait0 = 2u, kWait1 = 4u, kFirst = 8u, kCommit0 = 16u, kPostWait1 = 64u };
+enum : uint32_t { kFromOp = 1u, kWait0 = 2u, kWait1 = 4u, kFirst = 8u, kCommit0 = 16u, kPostWait1 = 64u, kOddRegion = 256u };
 constexpr int total_units() {
   int n = 0;
   for (int s = 0; s < kBwdSteps; ++s) n += bwd_step_info(s).k_atoms;
@@ -264,7 +271,8 @@ constexpr ProgTable make_prog() {
       if (ui.from_op) flags |= kFromOp;
       if (ui.group == 1 && first_g1) flags |= kWait0;
       if (ui.group == 2 && first_g2) flags |= kWait1;
-      if (u == 0) flags |= kFirst;
+      if (u == 0) flags |= kFirst;  // also: the step overwrites its region -> the savers must have read what lived there
+      if (s & 1) flags |= kOddRegion;
       if (ui.last) flags |= kCommit0;
       if (u == nu - 1 && !any_g2) flags |= kPostWait1;
       const uint32_t d_col = region_col_c(s);
@@ -308,6 +316,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
   const uint32_t bar_empty = bar_full + kNumSlots * 8;
   const uint32_t bar_aready = bar_empty + kNumSlots * 8;  // [2]
   const uint32_t bar_accfull = bar_aready + 16;           // [2] (only [0] used: one commit per step)
+  const uint32_t bar_sv = bar_accfull + 16;               // [half][step & 1]: the step's FP16 output is in TMEM -> savers
+  const uint32_t bar_saved = bar_sv + 32;                 // [region]: the savers have read the region -> MMA warp
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
 
   if (threadIdx.x == 0) {
@@ -318,6 +328,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar_aready + h * 8, kRowThreads / 32);
       mbar_init(bar_accfull + h * 8, 1);
+      mbar_init(bar_sv + h * 16, kRowThreads / 32);
+      mbar_init(bar_sv + h * 16 + 8, kRowThreads / 32);
+      mbar_init(bar_saved + h * 8, 4);
     }
     mbar_fence_init();
   }
@@ -342,6 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
 
   if (warp == 0) {
     // ============================== weight producer ==============================
+    reg_dec<kRegsLight>();
     uint32_t slot = 0, phase = 0, seq = 0;
     for (int j = 0; j < n_tiles_cta; ++j) {
       const int t = j % tpu;
@@ -362,11 +376,22 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
+    reg_dec<kRegsLight>();
     uint32_t slot = 0, phase = 0, ph_a0 = 0, ph_a1 = 0;
+    uint32_t sv_pending = 0, sv_phase = 0;  // per region bit: a step's output lives there / parity of bar_saved
     const uint64_t op_desc = umma_smem_desc_sw128(smem_base + kOffOp);
     for (int j = 0; j < n_tiles_cta; ++j) {
       for (int i = 0; i < kTileUnits; ++i) {
         const ProgEntry e = c_prog.e[i];
+        if (e.z & kFirst) {  // first unit of a step
+          const uint32_t rho = (e.z & kOddRegion) ? 1u : 0u;
+          if (sv_pending & (1u << rho)) {
+            mbar_wait(bar_saved + rho * 8, (sv_phase >> rho) & 1u);
+            sv_phase ^= 1u << rho;
+            tc_fence_after_sync();
+          }
+          sv_pending |= 1u << rho;
+        }
         if (e.z & kWait0) {
           mbar_wait(bar_aready, ph_a0);
           ph_a0 ^= 1;
@@ -402,11 +427,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         }
       }
     }
-  } else {
+  } else if (warp >= 4 && warp < 12) {
     // ============================== row warps ==============================
+    reg_inc<kRegsRow>();
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int ch = (warp - 2) >> 2;
+    const int ch = (warp - 4) >> 2;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t ph_acc = 0;
     const float scale = p.scal[0];
@@ -462,34 +488,35 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         mbar_wait(bar_accfull, ph_acc);
         ph_acc ^= 1;
         tc_fence_after_sync();
-        uint8_t* img = real ? rec + rec_dy_off(L) + img_row_base(W, row) : nullptr;
-        {  // half 0: output columns [64 ch, 64 ch + 64)
+        const uint32_t par = (uint32_t)(s & 1);
+        {  // half 0: output columns [64 ch, 64 ch + 64).  The FP16 result goes back to TMEM in place: A operand of the next step
+           // and (every step, also the last) what the saver warps write to the record.
           const int c0 = 64 * ch;
           uint32_t ha[16], hb[16];
           bwd_epi_slice(t_acc + c0, m0, ha, hb);
-          if (s < kBwdSteps - 1) {
-            tmem_st16(t_acc + c0, ha);
-            tmem_st16(t_acc + c0 + 16, hb);
-            tmem_wait_st();
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_aready);
+          tmem_st16(t_acc + c0, ha);
+          tmem_st16(t_acc + c0 + 16, hb);
+          tmem_wait_st();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if (s < kBwdSteps - 1) mbar_arrive(bar_aready);
+            mbar_arrive(bar_sv + par * 8);
           }
-          if (img) { store_t32(img, row, c0, ha); store_t32(img, row, c0 + 32, hb); }
         }
         if (two) {  // half 1: columns [128 + 64 ch, ...)
           const int c0 = 128 + 64 * ch;
           uint32_t ha[16], hb[16];
           bwd_epi_slice(t_acc + c0, m1, ha, hb);
-          if (s < kBwdSteps - 1) {
-            tmem_st16(t_acc + c0, ha);
-            tmem_st16(t_acc + c0 + 16, hb);
-            tmem_wait_st();
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_aready + 8);
+          tmem_st16(t_acc + c0, ha);
+          tmem_st16(t_acc + c0 + 16, hb);
+          tmem_wait_st();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if (s < kBwdSteps - 1) mbar_arrive(bar_aready + 8);
+            mbar_arrive(bar_sv + 16 + par * 8);
           }
-          if (img) { store_t32(img, row, c0, ha); store_t32(img, row, c0 + 32, hb); }
         } else if (s < kBwdSteps - 1) {
           tc_fence_before_sync();
           __syncwarp();
@@ -499,6 +526,55 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
       }
     }
     tc_fence_before_sync();
+  } else if (warp >= 12) {
+    // ============================== record savers ==============================
+    // bar_sv[half][s & 1] cannot run more than one phase ahead of this warp: the step that next completes the same barrier is
+    // s + 2 (or a step of the next tile in the same region), whose MMAs wait for bar_saved of step s.
+    reg_dec<kRegsSaver>();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t sv_ph = 0;  // bit (half * 2 + parity): phase of bar_sv[half][parity]
+    for (int j = 0; j < n_tiles_cta; ++j) {
+      const int unit = blockIdx.x + (j / tpu) * gridDim.x;
+      uint8_t* rec = unit < p.n_units ? p.rec + ((size_t)unit * tpu + (j % tpu)) * kRecBytes : nullptr;
+#pragma unroll 1
+      for (int s = 0; s < kBwdSteps; ++s) {
+        const int L = 8 - s, W = rec_width(L);
+        const uint32_t par = (uint32_t)(s & 1);
+        const uint32_t t_reg = t_lane + region_col(s);
+        uint8_t* img = rec ? rec + rec_dy_off(L) + img_row_base(W, row) : nullptr;
+        const int n_slices = W >> 6;
+#pragma unroll 1
+        for (int i = 0; i < n_slices; ++i) {
+          if ((i & 1) == 0) {
+            const int h = i >> 1;
+            const uint32_t bit = 1u << (h * 2 + par);
+            mbar_wait(bar_sv + h * 16 + par * 8, (sv_ph & bit) ? 1u : 0u);
+            sv_ph ^= bit;
+            tc_fence_after_sync();
+          }
+          uint32_t v[32];
+          tmem_ld32(t_reg + 64 * i, v);
+          tmem_wait_ld();
+          if (i == n_slices - 1) {  // the whole region has been read
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_saved + par * 8);
+          }
+          if (img) {
+            uint32_t h0[16], h1[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { h0[k] = v[k]; h1[k] = v[16 + k]; }
+            store_t32(img, row, 64 * i, h0);
+            store_t32(img, row, 64 * i + 32, h1);
+          }
+        }
+      }
+    }
+    tc_fence_before_sync();
+  } else {
+    reg_dec<kRegsLight>();  // warps 2, 3: idle, but setmaxnreg is a warpgroup-wide instruction
   }
 
   __syncthreads();
