@@ -467,12 +467,13 @@ int nfb_render_backward(NfbHandle* h, const NfbOutGrads* og, const float* const 
     c.wstream[0] = h->net[0].stream_bwd;
     c.wstream[1] = fine ? h->net[1].stream_bwd : h->net[0].stream_bwd;
     NFB_CUDA(nfb::launch_chain(c, h->num_sms, st, &h->launches));
-    for (int net = 0; net < (fine ? 2 : 1); ++net) {
-      nfb::DwParams d;
+    {
+      nfb::DwParams d = {};
       d.rec = tr.rec; d.n_units = n_units; d.tpu = tr.tiles_c + tr.tiles_f;
-      d.t_base = net ? tr.tiles_c : 0; d.t_cnt = net ? tr.tiles_f : tr.tiles_c;
-      d.acc = tr.acc[net]; d.scal = tr.scal;
-      NFB_CUDA(nfb::launch_dw(d, h->num_sms, st, &h->launches));
+      d.t_base[0] = 0; d.t_cnt[0] = tr.tiles_c;
+      d.t_base[1] = tr.tiles_c; d.t_cnt[1] = fine ? tr.tiles_f : 0;
+      d.acc[0] = tr.acc[0]; d.acc[1] = tr.acc[1]; d.scal = tr.scal;
+      NFB_CUDA(nfb::launch_dw(d, h->num_sms, st, &h->launches));  // both networks in one launch
     }
     return NFB_OK;
   };

@@ -79,10 +79,12 @@ struct ChainParams {
   const float* scal;            // [0] = loss scale, [1] = 1 / scale
   const uint8_t* wstream[2];    // backward weight streams (coarse, fine)
 };
-struct DwParams {
+struct DwParams {  // ONE launch covers both networks: the first parts[0] * groups CTAs work on network 0, the rest on network 1
   const uint8_t* rec;
-  int n_units, tpu, t_base, t_cnt;  // tiles of this network: unit * tpu + t_base + [0, t_cnt)
-  float* acc;
+  int n_units, tpu;
+  int t_base[2], t_cnt[2];  // tiles of network i: unit * tpu + t_base[i] + [0, t_cnt[i])
+  int parts[2];             // CTAs per job group of network i (set by launch_dw, proportional to the tile counts)
+  float* acc[2];
   const float* scal;
 };
 // host copies of the compile-time schedules (nfb_debug_schedule); index < 0: number of entries; else words written or -1

@@ -17,16 +17,17 @@ namespace nfb {
 //   W6[n][k], n < 128: (Wd0[:, :256] @ Wf)[n][k];  n == 128: (wa @ Wf)[k];  n > 128: 0
 //   b6[n],    n < 128: bd0[n] + Wd0[n, :256] . bf;  n == 128: ba + wa . bf
 struct NetParams { const float* p[26]; const float* w6; const float* b6; };  // state_dict order (nfb.h: nfb_load_weights) + the fold
-__device__ __forceinline__ float w6_elem(const NetParams& a, int n, int k) {
-  if (n > 128) return 0.f;
+// One quarter (j in [64 jq, 64 jq + 64)) of the dot product behind W6[n][k], four independent FP64 chains.
+__device__ __forceinline__ double w6_quarter(const NetParams& a, int n, int k, int jq) {
   const float* left = (n < 128) ? (a.p[16] + (size_t)n * 280) : a.p[14];
   const float* Wf = a.p[12];
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};  // four independent chains: the loop is bound by the FP64 add latency
-  for (int j = 0; j < 256; j += 4) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+  for (int j = 64 * jq; j < 64 * jq + 64; j += 4) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[q] += (double)left[j + q] * (double)Wf[(j + q) * 256 + k];
   }
-  return (float)((acc[0] + acc[1]) + (acc[2] + acc[3]));
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 __device__ __forceinline__ float b6_elem(const NetParams& a, int n) {
   if (n > 128) return 0.f;
@@ -36,14 +37,18 @@ __device__ __forceinline__ float b6_elem(const NetParams& a, int n) {
   for (int j = 0; j < 256; ++j) b += (double)left[j] * (double)bf[j];
   return (float)b;
 }
-// Launch 1 of a re-pack: W6 [144][256] and b6 [144] of up to two networks (blockIdx.y); thread = (row n = blockIdx.x, column k):
-// the j loop reads left[j] as a warp broadcast and Wf[j][k] coalesced.
+// Launch 1 of a re-pack: W6 [144][256] and b6 [144] of up to two networks (blockIdx.z).  Block = row n (blockIdx.x) x 64 columns
+// (blockIdx.y) x the four quarters of the 256-long dot product (threadIdx.x >> 6): short FP64 chains, Wf[j][k] coalesced over k,
+// left[j] a warp broadcast; the quarters are summed in a fixed order through shared memory.
 struct FoldArgs { NetParams net[2]; float* w6[2]; float* b6[2]; };
 __global__ void __launch_bounds__(256) fold_feat_kernel(const FoldArgs f) {
-  const NetParams& a = f.net[blockIdx.y];
-  const int n = blockIdx.x, k = threadIdx.x;
-  f.w6[blockIdx.y][n * 256 + k] = w6_elem(a, n, k);
-  if (k == 0) f.b6[blockIdx.y][n] = b6_elem(a, n);
+  __shared__ double part[4][64];
+  const NetParams& a = f.net[blockIdx.z];
+  const int n = blockIdx.x, kq = threadIdx.x & 63, jq = threadIdx.x >> 6, k = blockIdx.y * 64 + kq;
+  part[jq][kq] = (n <= 128) ? w6_quarter(a, n, k, jq) : 0.0;
+  __syncthreads();
+  if (jq == 0) f.w6[blockIdx.z][n * 256 + k] = (float)((part[0][kq] + part[1][kq]) + (part[2][kq] + part[3][kq]));
+  if (threadIdx.x == 0 && blockIdx.y == 0) f.b6[blockIdx.z][n] = b6_elem(a, n);
 }
 
 // step -> (source parameter index, leading dimension, valid output rows); step 6 is the folded matrix
@@ -237,7 +242,7 @@ cudaError_t launch_repack(NetBuffers* const nb[2], const float* const* const par
     a.x1[n] = nb[n]->stream_x1; a.x3[n] = nb[n]->stream_x3; a.bwd[n] = nb[n]->stream_bwd;
     a.bias_static[n] = nb[n]->bias_static; a.w0c[n] = nb[n]->w0c; a.w3c[n] = nb[n]->w3c; a.wd0b_t[n] = nb[n]->wd0b_t;
   }
-  fold_feat_kernel<<<dim3(144, n_nets), 256, 0, st>>>(f);
+  fold_feat_kernel<<<dim3(144, 4, n_nets), 256, 0, st>>>(f);
   ++*launches;
   repack_kernel<<<dim3(kRepackBlocks, n_nets), 256, 0, st>>>(a);
   ++*launches;

@@ -658,10 +658,14 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
   if ((smem_base & 1023u) != 0u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // this CTA: job group (blockIdx.x % kGroups) x a contiguous share of the network's tiles
-  const int parts = (int)gridDim.x / kGroups;
-  const int group = (int)blockIdx.x % kGroups, part = (int)blockIdx.x / kGroups;
-  const int total = p.n_units * p.t_cnt;
+  // this CTA: network x job group (blockIdx.x % kGroups) x a contiguous share of the network's tiles
+  const int group = (int)blockIdx.x % kGroups;
+  int part = (int)blockIdx.x / kGroups;
+  const int net = (part >= p.parts[0]) ? 1 : 0;
+  if (net) part -= p.parts[0];
+  const int parts = p.parts[net];
+  const int t_cnt = p.t_cnt[net], t_base = p.t_base[net];
+  const int total = p.n_units * t_cnt;
   const int per = (total + parts - 1) / parts;
   const int j0 = part * per;
   const int j1 = min(total, j0 + per);
@@ -696,8 +700,8 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr_s;
 
   auto tile_rec = [&](int j) -> const uint8_t* {
-    const int u = j / p.t_cnt, t = j - u * p.t_cnt;
-    return p.rec + ((size_t)u * p.tpu + p.t_base + t) * kRecBytes;
+    const int u = j / t_cnt, t = j - u * t_cnt;
+    return p.rec + ((size_t)u * p.tpu + t_base + t) * kRecBytes;
   };
 
   if (warp == 0) {
@@ -765,7 +769,7 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
       mbar_wait(bar_accfull, acc_phase);
       acc_phase ^= 1;
       tc_fence_after_sync();
-      float* out = p.acc + J.out_off + (size_t)(J.out_row0 + row) * J.out_ld;
+      float* out = p.acc[net] + J.out_off + (size_t)(J.out_row0 + row) * J.out_ld;
       if (J.b_rows == 16) {
         uint32_t v[16];
         tmem_ld16(t_lane, v);
@@ -785,7 +789,7 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
         uint32_t v[4];
         tmem_ld4(t_lane + kBiasCol, v);
         tmem_wait_ld();
-        atomicAdd(p.acc + acc_bias_off(J.bias_layer) + J.out_row0 + row, __uint_as_float(v[0]) * inv);
+        atomicAdd(p.acc[net] + acc_bias_off(J.bias_layer) + J.out_row0 + row, __uint_as_float(v[0]) * inv);
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -1012,13 +1016,22 @@ cudaError_t launch_chain(const ChainParams& p, int num_sms, cudaStream_t st, lon
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-cudaError_t launch_dw(const DwParams& p, int num_sms, cudaStream_t st, long long* launches) {
-  const int total = p.n_units * p.t_cnt;
-  if (total <= 0) return cudaSuccess;
-  int parts = num_sms / dw::kGroups;  // CTAs per job group (18 on a 148-SM B200: 144 CTAs)
-  if (parts > total) parts = total;
+cudaError_t launch_dw(const DwParams& p_in, int num_sms, cudaStream_t st, long long* launches) {
+  DwParams p = p_in;
+  const long long tot0 = (long long)p.n_units * p.t_cnt[0], tot1 = (long long)p.n_units * p.t_cnt[1];
+  if (tot0 + tot1 <= 0) return cudaSuccess;
+  int parts = num_sms / dw::kGroups;  // CTAs per job group over both networks (18 on a 148-SM B200: 144 CTAs)
   if (parts < 1) parts = 1;
-  dw::dw_kernel<<<parts * dw::kGroups, dw::kThreads, dw::kSmemBytes, st>>>(p);
+  // split them in proportion to the networks' tile counts (64c + 64f: 1 : 2 -> 6 + 12, 171 tiles per CTA either way)
+  int p0 = tot1 == 0 ? parts : (tot0 == 0 ? 0 : (int)((parts * tot0 + (tot0 + tot1) / 2) / (tot0 + tot1)));
+  if (tot0 > 0 && p0 < 1) p0 = 1;
+  if (tot1 > 0 && p0 > parts - 1) p0 = parts - 1;
+  int p1 = tot1 > 0 ? parts - p0 : 0;
+  if (p0 > tot0) p0 = (int)tot0;
+  if (p1 > tot1) p1 = (int)tot1;
+  if (p0 + p1 < 1) return cudaSuccess;
+  p.parts[0] = p0; p.parts[1] = p1;
+  dw::dw_kernel<<<(p0 + p1) * dw::kGroups, dw::kThreads, dw::kSmemBytes, st>>>(p);
   ++*launches;
   return cudaGetLastError();
 }
