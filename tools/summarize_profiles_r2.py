@@ -100,13 +100,16 @@ def launch_list(tag, csv_name, title, command, note):
     path = os.path.join(G, csv_name)
     if not os.path.exists(path):
         return
-    rows = [r for r in csv.reader(open(path)) if len(r) > 14 and r[0].isdigit()]
+    allrows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr = allrows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    to_ns = {"ns": 1.0, "nsecond": 1.0, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6, "s": 1e9, "second": 1e9}
     agg = collections.OrderedDict()
-    for r in rows:
-        name = r[4].split("(")[0]
+    for r in allrows[1:]:
+        name = r[ki].split("(")[0]
         agg.setdefault(name, [0, 0.0])
         agg[name][0] += 1
-        agg[name][1] += float(r[14])
+        agg[name][1] += float(r[vi].replace(",", "")) * to_ns.get(r[ui], 1.0)
     tot = sum(v[1] for v in agg.values()) or 1.0
     lines = [f"# ncu launch list — {title}", "", f"`{command}`", "", note, "", "| kernel | launches | total ms | share |", "|---|---|---|---|"]
     for k, v in agg.items():
@@ -141,8 +144,36 @@ def sass_summary():
     print("wrote r2_sass_summary")
 
 
+def r2c():
+    """The training kernels as shipped at the end of round 2 (tools/profile_r2c.sh)."""
+    T = "python tools/train_bench.py --steps 2 --warmup 2 --impl fused"
+    summarize("r2c_dw_kernel_ncu", "prof_r2c_dw_kernel.ncu-rep",
+              "`nfb::dw::dw_kernel` (weight-gradient GEMMs, BOTH networks in one launch, 8 job groups), 2048 rays 64c+64f",
+              f"ncu --set full --clock-control none --import-source on -k regex:dw_kernel -s 2 -c 1 {T}")
+    summarize("r2c_chain_kernel_ncu", "prof_r2c_chain_kernel.ncu-rep", "`nfb::chain::chain_kernel` (dX chain, record-saver warps), 2048 rays 64c+64f",
+              f"ncu --set full ... -k regex:chain_kernel -s 2 -c 1 {T}")
+    summarize("r2c_fwd_save_ncu", "prof_r2c_render_kernel.ncu-rep", "`nfb::render_kernel<fast, SAVE>` (training forward, record-saver warps), 2048 rays 64c+64f",
+              f"ncu --set full ... -k regex:render_kernel -s 2 -c 1 {T}")
+    launch_list("r2c_train_launches", "train_launches_r2c.csv", "training iterations as shipped (`tools/train_bench.py --impl fused`, launches 70-170 of the run)",
+                "ncu --metrics gpu__time_duration.sum --clock-control none -s 70 -c 100 python tools/train_bench.py --steps 4 --warmup 3 --impl fused",
+                "One iteration = frame_fold, 4 torch RNG kernels (the reference's noise draws), render_kernel<SAVE>, loss_grad, composite_bwd + scale, "
+                "chain, ONE dw launch (both networks), finalize + fin_dir0, adam, fold_feat + repack (+ memsets; the index kernels are the bench's batch gathers).")
+    sass_summary()
+    for src in ("r2c_bench_n1.json", "r2c_train_bench_n1.json"):
+        if os.path.exists(os.path.join(G, src)) and os.path.getsize(os.path.join(G, src)) > 0:
+            shutil.copy(os.path.join(G, src), os.path.join(P, src))
+    log = os.path.join(G, "r2c_gputests.log")
+    if os.path.exists(log):
+        tail = open(log).read().strip().splitlines()[-3:]
+        open(os.path.join(P, "r2c_gputests.txt"), "w").write("python -m pytest tests -m gpu -q -x --timeout 100   (1 x B200, tools/profile_r2c.sh)\n" + "\n".join(tail) + "\n")
+
+
 if __name__ == "__main__":
     os.makedirs(P, exist_ok=True)
+    import sys
+    if "--r2c" in sys.argv:
+        r2c()
+        raise SystemExit(0)
     B = "python bench.py --no-extras --no-cpu-baseline --steps 1 --warmup 1"
     flop512 = 262144 * 256 * 1100032
     summarize("r2_render3_kernel_ncu", "prof_r2_render3.ncu-rep", "`nfb::v7::render3_kernel` (fast mode, shipped default), 512x512, 64c+128f",
