@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--num-fine", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip rows / train / gpu_baseline / exact / stress records")
+    ap.add_argument("--extras", default="all", help="comma list out of rows,rows_1024,train,single (exact / stress / gpu_baseline); default all")
     ap.add_argument("--train-impl", default=os.environ.get("NFB_TRAIN_IMPL", "fused"), choices=["fused", "dropin"])
     ap.add_argument("--no-train-graph", action="store_true", help="fused training step launch by launch instead of one CUDA graph replay")
     return ap.parse_args()
@@ -578,17 +579,21 @@ def main():
 
     # ---- sub-records (collectives inside: every rank takes part)
     extras = {}
+    want = (lambda k: a.extras == "all" or k in a.extras.split(","))  # noqa: E731
     if not a.no_extras:
-        extras["rows"] = bench_rows(c, 512, 512, 64, 128, a.steps, a.warmup, a.precision)
-        extras["rows_1024"] = bench_rows(c, 1024, 1024, 128, 256, max(3, min(a.steps, 5)), 1, a.precision)
-        try:
-            extras["train"] = bench_train(c, a.steps, a.warmup, a.train_impl, graph=not a.no_train_graph)
-        except Exception as e:  # a training-path failure must not take the headline down
-            extras["train"] = {"unavailable": repr(e)[:300]}
-            if world > 1:
-                raise
+        if want("rows"):
+            extras["rows"] = bench_rows(c, 512, 512, 64, 128, a.steps, a.warmup, a.precision)
+        if want("rows_1024"):
+            extras["rows_1024"] = bench_rows(c, 1024, 1024, 128, 256, max(3, min(a.steps, 5)), 1, a.precision)
+        if want("train"):
+            try:
+                extras["train"] = bench_train(c, a.steps, a.warmup, a.train_impl, graph=not a.no_train_graph)
+            except Exception as e:  # a training-path failure must not take the headline down
+                extras["train"] = {"unavailable": repr(e)[:300]}
+                if world > 1:
+                    raise
         eng.sync_weights(mc, mf)
-        if rank == 0 and world == 1:
+        if rank == 0 and world == 1 and want("single"):
             # exact mode (FP16 hi+lo x3) on the headline workload: the mode that holds 1e-4 on trained-like weights
             for _ in range(2):
                 step_resident(0)
