@@ -11,11 +11,13 @@
 //   2. chain_kernel           dX chain of the MLP per 128-row tile on tcgen05: 9 steps with transposed weight streams,
 //                             same machinery as the forward kernel (TMEM-resident activations converted in place, bulk-copy
 //                             weight ring with cluster multicast, two-gate epilogue).  The epilogue applies the saved ReLU
-//                             masks and writes every dY as a transposed FP16 image into the tile record.
+//                             masks; four record-saver warps read every dY back from TMEM and write it as a transposed FP16
+//                             image into the tile record.
 //   3. dw_kernel              dW[n,k] = sum_rows dY[row,n] X[row,k] for every layer: both operands are bulk-copied from
 //                             the tile records (K-major images whose K axis is the sample row) and multiplied on tcgen05
 //                             (M=128 output features x N input features per job, FP32 accumulation in TMEM over all tiles
-//                             of the CTA), then reduced into FP32 accumulators with red.global.add.
+//                             of the CTA), then reduced into FP32 accumulators with red.global.add.  One launch for both
+//                             networks; HBM-bound, so the job groups are laid out for L2 sharing of the input images.
 //   4. finalize_kernel        un-folds the kernel's parametrisation (fc_feat pre-multiplied into fc_alpha / layers_dir.0,
 //                             conditioning columns folded into biases) by the chain rule and writes the 24 used parameter
 //                             gradients of each network in the reference's state_dict layout, plus d latent_code.
