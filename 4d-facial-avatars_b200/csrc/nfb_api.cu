@@ -657,6 +657,7 @@ int nfb_debug_schedule(int which, int index, uint32_t* out, int out_words) {
     case 1: return nfb::debug_prog_v6(index, out);
     case 2: return nfb::debug_prog_chain(index, out);
     case 3: return nfb::debug_jobs_dw(index, out);
+    case 4: return index < 0 ? 1 : nfb::debug_dw_split(out);  // in/out: {num_sms, tiles 0, tiles 1} -> {parts0, parts1, groups}
     default:
       if (which >= 1000) {  // 1000 + n_iter * 100 + Tc * 10 + Tf: the pipelined kernel's job sequence
         const int w = which - 1000;

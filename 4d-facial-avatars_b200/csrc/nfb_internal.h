@@ -93,6 +93,7 @@ int debug_prog_v6(int index, uint32_t* out);
 int debug_jobs_v7(int n_iter, int tc, int tf, int index, uint32_t* out);
 int debug_prog_chain(int index, uint32_t* out);
 int debug_jobs_dw(int index, uint32_t* out);
+int debug_dw_split(uint32_t* io);  // io: {num_sms, tiles net 0, tiles net 1} -> {parts0, parts1, groups}
 cudaError_t train_kernels_setup();
 cudaError_t launch_composite_bwd(const CompBwdParams& q, float* scal, cudaStream_t st, long long* launches);
 cudaError_t launch_chain(const ChainParams& p, int num_sms, cudaStream_t st, long long* launches);

@@ -1018,22 +1018,36 @@ cudaError_t launch_chain(const ChainParams& p, int num_sms, cudaStream_t st, lon
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-cudaError_t launch_dw(const DwParams& p_in, int num_sms, cudaStream_t st, long long* launches) {
-  DwParams p = p_in;
-  const long long tot0 = (long long)p.n_units * p.t_cnt[0], tot1 = (long long)p.n_units * p.t_cnt[1];
-  if (tot0 + tot1 <= 0) return cudaSuccess;
-  int parts = num_sms / dw::kGroups;  // CTAs per job group over both networks (18 on a 148-SM B200: 144 CTAs)
+// CTAs per job group for the two networks: `num_sms / kGroups` parts split in proportion to the networks' tile counts
+// (64c + 64f: 1 : 2 -> 6 + 12 on 148 SMs, 171 tiles per CTA either way), at least one part per non-empty network, never more
+// parts than tiles.  Host logic, exposed to the tests through nfb_debug_schedule(4, ...).
+void dw_split(int num_sms, long long tot0, long long tot1, int* parts0, int* parts1) {
+  int parts = num_sms / dw::kGroups;
   if (parts < 1) parts = 1;
-  // split them in proportion to the networks' tile counts (64c + 64f: 1 : 2 -> 6 + 12, 171 tiles per CTA either way)
-  int p0 = tot1 == 0 ? parts : (tot0 == 0 ? 0 : (int)((parts * tot0 + (tot0 + tot1) / 2) / (tot0 + tot1)));
+  if (tot0 > 0 && tot1 > 0 && parts < 2) parts = 2;  // CTAs are independent: more CTAs than SMs only serialises them
+  int p0 = tot1 <= 0 ? (tot0 > 0 ? parts : 0) : (tot0 <= 0 ? 0 : (int)((parts * tot0 + (tot0 + tot1) / 2) / (tot0 + tot1)));
   if (tot0 > 0 && p0 < 1) p0 = 1;
   if (tot1 > 0 && p0 > parts - 1) p0 = parts - 1;
   int p1 = tot1 > 0 ? parts - p0 : 0;
   if (p0 > tot0) p0 = (int)tot0;
   if (p1 > tot1) p1 = (int)tot1;
-  if (p0 + p1 < 1) return cudaSuccess;
-  p.parts[0] = p0; p.parts[1] = p1;
-  dw::dw_kernel<<<(p0 + p1) * dw::kGroups, dw::kThreads, dw::kSmemBytes, st>>>(p);
+  *parts0 = p0;
+  *parts1 = p1;
+}
+int debug_dw_split(uint32_t* io) {  // in: num_sms, tiles of network 0, tiles of network 1; out: parts0, parts1, groups
+  int p0 = 0, p1 = 0;
+  dw_split((int)io[0], (long long)io[1], (long long)io[2], &p0, &p1);
+  io[0] = (uint32_t)p0; io[1] = (uint32_t)p1; io[2] = (uint32_t)dw::kGroups;
+  return 3;
+}
+
+cudaError_t launch_dw(const DwParams& p_in, int num_sms, cudaStream_t st, long long* launches) {
+  DwParams p = p_in;
+  const long long tot0 = (long long)p.n_units * p.t_cnt[0], tot1 = (long long)p.n_units * p.t_cnt[1];
+  if (tot0 + tot1 <= 0) return cudaSuccess;
+  dw_split(num_sms, tot0, tot1, &p.parts[0], &p.parts[1]);
+  if (p.parts[0] + p.parts[1] < 1) return cudaSuccess;
+  dw::dw_kernel<<<(p.parts[0] + p.parts[1]) * dw::kGroups, dw::kThreads, dw::kSmemBytes, st>>>(p);
   ++*launches;
   return cudaGetLastError();
 }

@@ -313,7 +313,8 @@ int nfb_render_frame_host(NfbHandle* h, const float pose[12], const double intri
 /* Test hook, host only (no CUDA call): the compile-time schedules the kernels execute.  which: 0 = one-tile render program,
  * 1 = two-tile render program (word 4 = half-step group), 2 = backward chain program (each: idesc, TMEM columns, flags,
  * (stream offset / 16) | rows << 20), 3 = weight-gradient jobs (a_off, a_rows, a_half, b_off, b_rows, bias_layer, out_off,
- * out_ld, out_row0, group), 1000 + 100 n_iter + 10 Tc + Tf = the pipelined render kernel's job sequence for a CTA with n_iter units of work and
+ * out_ld, out_row0, group), 4 = the CTA split of the weight-gradient launch (in/out: out[0..2] = SMs, tiles of network 0, tiles of
+ * network 1 -> parts of network 0, parts of network 1, job groups per part), 1000 + 100 n_iter + 10 Tc + Tf = the pipelined render kernel's job sequence for a CTA with n_iter units of work and
  * Tc / Tf tile pairs per pass (unit iteration, pass, tile, then the kernel's shared-memory bytes and row limits).  index < 0: returns the number of entries; otherwise fills out[0..] (out_words >= 10) and returns
  * the number of words written, or -1. */
 int nfb_debug_schedule(int which, int index, uint32_t* out, int out_words);

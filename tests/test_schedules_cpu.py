@@ -157,3 +157,22 @@ def test_pipelined_kernel_job_sequence(lib, n_iter, tc, tf):
             assert pos[(u + 1, 0, 0)] < pos[(u, 1, 0)]                        # C(u+1) before F(u, 0)
         if u + 2 < n_iter:
             assert pos[(u + 2, 0, 0)] > pos[(u, 1, tf - 1)]                   # ... but C(u+2) only after F(u) has been issued
+
+
+@pytest.mark.parametrize("sms,t0,t1", [(148, 1024, 2048), (148, 128, 256), (148, 24, 48), (148, 5, 0), (148, 1, 2), (148, 3, 1000),
+                                        (148, 1000, 3), (8, 10, 20), (132, 2048, 2048), (148, 0, 7)])
+def test_weight_gradient_cta_split(lib, sms, t0, t1):
+    """launch_dw's host logic (csrc/nfb_train.cu: dw_split): the CTAs of the one weight-gradient launch are split between the two
+    networks in proportion to their tile counts; every non-empty network gets at least one part, never more parts than tiles,
+    and the 64c+64f training batch (1024 + 2048 tiles) gets 6 + 12 parts of 8 CTAs = the same 171 tiles per CTA."""
+    buf = (C.c_uint32 * 16)(sms, t0, t1)
+    assert lib.nfb_debug_schedule(4, 0, buf, 16) == 3
+    p0, p1, groups = int(buf[0]), int(buf[1]), int(buf[2])
+    assert groups == 8
+    assert (p0 >= 1) == (t0 > 0) and (p1 >= 1) == (t1 > 0)
+    assert p0 <= max(t0, 0) and p1 <= max(t1, 0)
+    assert (p0 + p1) * groups <= max(sms, 16)
+    if (sms, t0, t1) == (148, 1024, 2048):
+        assert (p0, p1) == (6, 12) and -(-t0 // p0) == -(-t1 // p1) == 171
+    if t0 > 0 and t1 > 0 and min(t0, t1) >= 18:  # proportional within one part
+        assert abs(p0 / (p0 + p1) - t0 / (t0 + t1)) <= 1.0 / (p0 + p1)
