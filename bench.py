@@ -356,10 +356,14 @@ def bench_train(c, steps, warmup, impl, rays=2048, nc=64, nf=64, graph=True):
             w, r = (world, rank) if shard else (1, 0)
             per = rays // w
             sel = idx[i][r * per:(r + 1) * per]
-            if graph:  # the whole iteration (incl. the all-reduce) is ONE graph replay; re-captured when the shard size changes
+            if graph and not captured.get("failed"):  # the whole iteration (incl. the all-reduce) is ONE graph replay; re-captured when the shard size changes
                 if captured["shard"] != shard:
-                    tr.capture(per, has_background=True, world=w, n_total=rays)
-                    captured["shard"] = shard
+                    try:
+                        tr.capture(per, has_background=True, world=w, n_total=rays)
+                        captured["shard"] = shard
+                    except Exception as e:  # same on every rank: fall back to launch-by-launch steps and say so in the record
+                        captured["failed"] = repr(e)[:200]
+                        return step(i, shard, ev)
                 if ev is not None:
                     ev[0].record()
                     ev[1].record()
@@ -427,6 +431,9 @@ def bench_train(c, steps, warmup, impl, rays=2048, nc=64, nf=64, graph=True):
     flop = 3 * ALGO_FLOP_PER_EVAL * (2 * nc + nf) * rays
     rec["roofline_frac"] = flop / (rec["ms_per_step"] * 1e-3) / 1e12 / c.peak / world
     rec["gpu_launches_total"] = c.eng.launch_count() - launches_before
+    if impl == "fused" and graph and captured.get("failed"):
+        rec["impl"] = impl + " (launch by launch: graph capture failed)"
+        rec["graph_capture_error"] = captured["failed"]
     return rec
 
 
