@@ -67,3 +67,30 @@ def test_meshgrid_minibatches_and_metrics(both):
     assert torch.equal(ref.img2mse(x, y), nerf.img2mse(x, y))
     for m in (0.0, 1e-5, 0.0123, 1.0):
         assert ref.mse2psnr(m) == nerf.mse2psnr(m)
+
+
+def test_cfgnode_on_the_shipped_yaml(both):
+    """The scripts build `CfgNode(yaml.load(...))`, read nested attributes and write `cfg.dump()` next to the checkpoints
+    (train_transformed_rays.py:46-50, 126-128): same tree, same leaves, a dump that loads back to the same dict."""
+    import yaml
+    nerf, ref = both
+    path = ref_loader.script_path(os.path.join("config", "dave", "dave_dvp_lcode_fixed_bg_512_paper_model.yml"))
+    raw = yaml.load(open(path), Loader=yaml.FullLoader)
+    a, b = ref.CfgNode(raw), nerf.CfgNode(raw)
+
+    def walk(x, y, trail):
+        assert set(x.keys()) == set(y.keys()), trail
+        for k in x.keys():
+            u, v = getattr(x, k), getattr(y, k)
+            if isinstance(u, dict):
+                assert isinstance(v, dict) and isinstance(v, nerf.CfgNode), trail + [k]
+                walk(u, v, trail + [k])
+            else:
+                assert u == v and type(u) is type(v), (trail + [k], u, v)
+
+    walk(a, b, [])
+    assert b.nerf.train.num_coarse == 64 and b.nerf.validation.num_fine == 64 and b.dataset.no_ndc is True
+    assert getattr(b.nerf, "train").chunksize == a.nerf.train.chunksize
+    assert yaml.safe_load(b.dump()) == yaml.safe_load(a.dump()) == raw
+    with pytest.raises(AttributeError):
+        b.nerf.no_such_option
