@@ -94,3 +94,28 @@ def test_cfgnode_on_the_shipped_yaml(both):
     assert yaml.safe_load(b.dump()) == yaml.safe_load(a.dump()) == raw
     with pytest.raises(AttributeError):
         b.nerf.no_such_option
+
+
+def test_model_class_against_the_reference_class(both):
+    """ConditionalBlendshapePaperNeRFModel built with the keyword arguments the scripts pass (train_transformed_rays.py:150-176):
+    same state_dict keys / shapes / dtypes, a reference checkpoint loads into the drop-in and back (strict), the torch forward of
+    the drop-in (not the hot path) returns the reference module's values bit for bit, and the attributes the scripts and the
+    renderer read are the same."""
+    nerf, ref = both
+    kw = dict(num_layers=8, hidden_size=256, skip_connect_every=3, num_encoding_fn_xyz=10, num_encoding_fn_dir=4,
+              include_input_xyz=True, include_input_dir=False, use_viewdirs=True, include_expression=True, latent_code_dim=32)
+    torch.manual_seed(11)
+    m_ref = ref.models.ConditionalBlendshapePaperNeRFModel(**kw)
+    m = nerf.models.ConditionalBlendshapePaperNeRFModel(**kw)
+    sd_ref, sd = m_ref.state_dict(), m.state_dict()
+    assert [(k, tuple(v.shape), v.dtype) for k, v in sd_ref.items()] == [(k, tuple(v.shape), v.dtype) for k, v in sd.items()]
+    m.load_state_dict(sd_ref, strict=True)
+    m_ref.load_state_dict(m.state_dict(), strict=True)
+    for name in ("dim_xyz", "dim_dir", "dim_expression", "dim_latent_code", "use_viewdirs"):
+        assert getattr(m, name) == getattr(m_ref, name), name
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(19, m.dim_xyz + m.dim_dir, generator=g)
+    expr, lat = torch.randn(76, generator=g), torch.randn(32, generator=g)
+    with torch.no_grad():
+        assert torch.equal(m(x, expr, lat), m_ref(x, expr, lat))
+    assert sum(p.numel() for p in m.parameters()) == sum(p.numel() for p in m_ref.parameters())
